@@ -1,0 +1,472 @@
+/*
+ * ORACLE -- TEST INFRASTRUCTURE ONLY.  Not shipped, not on the product path.
+ *
+ * CPU restatement (plain C + OpenMP, build with -ffp-contract=off) of the
+ * reference's 2-D matrix-free geometric multigrid for (lap - c) u = f, its
+ * unpreconditioned CG, and the Navier-Stokes step that calls them.
+ *
+ * Reference lines followed (all under /root/reference):
+ *   scripts-part2/multigrid.jl:25-38     preallocate_buffers (level sizes, lambda_x/lambda_y)
+ *   scripts-part2/multigrid.jl:41-84     MGsolve_2DPoisson!
+ *   scripts-part2/multigrid.jl:91-170    Vcycle_2DPoisson!
+ *   scripts-part2/multigrid.jl:173-188   residual_2DPoisson!
+ *   scripts-part2/multigrid.jl:245-258   iteration_2DPoisson! (damped Jacobi)
+ *   scripts-part2/multigrid.jl:269-297   iteration_2DPoisson_gs! (serial lexicographic GS, unused upstream)
+ *   scripts-part2/multigrid.jl:330-358   restrict! / restrict_wrapper! (injection)
+ *   scripts-part2/multigrid.jl:365-396, 427-472  prolongate (scatter, CPU loop order)
+ *   scripts-part2/krylov.jl:7-13, 55-91  matvec, cg!
+ *   scripts-part2/part2_utils.jl:11-39   load, boundary conditions
+ *   scripts-part2/part2.jl:58-137, 140-262  init, dt rule, stencil kernels, time step
+ *
+ * Variant B (red-black Gauss-Seidel + full weighting) is a north-star
+ * extension with NO reference implementation: "parity unpinned" for it; this
+ * file is its only definition.
+ *
+ * Parity of variant A is PINNED by test/reftest-files/fortran/{S,T,W}.bin
+ * (tests/test_oracle_multigrid.py); the beta>0 path and apply_BCs=true
+ * branches are "parity unpinned" (no reference artefact exercises them).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_COARSE_JACOBI 0
+#define ORC_COARSE_CG 1
+#define ORC_SMOOTH_JACOBI 0
+#define ORC_SMOOTH_RBGS 1
+#define ORC_RESTRICT_INJECT 0
+#define ORC_RESTRICT_FW 1
+
+typedef struct {
+    int coarse_solve_size; /* MGOpt.coarse_solve_size (multigrid.jl:17) */
+    int coarse_solver;     /* MGOpt.coarse_solver */
+    int smoother;          /* variant A: Jacobi; variant B: RB-GS */
+    int restriction;       /* variant A: injection; variant B: full weighting */
+    int unfused;           /* 1: separate residual / square / sum / axpy passes like the reference */
+} orc_mg_opt;
+
+#define IDX(i, j) ((size_t)(i) + (size_t)nx * (j))
+
+/* ---- counters so tests can assert sweep counts on the coarsest level ---- */
+static long g_coarse_sweeps_last = 0;
+long orc_mg_last_coarse_sweeps(void) { return g_coarse_sweeps_last; }
+
+/* part2_utils.jl:26-31 */
+void orc_bc_dirichlet(double *T, int nx, int ny)
+{
+    for (int i = 0; i < nx; ++i) { T[IDX(i, 0)] = 1.0; T[IDX(i, ny - 1)] = 0.0; }
+}
+/* part2_utils.jl:34-39 */
+void orc_bc_neumann(double *T, int nx, int ny)
+{
+    for (int j = 0; j < ny; ++j) T[IDX(0, j)] = T[IDX(1, j)];
+    for (int j = 0; j < ny; ++j) T[IDX(nx - 1, j)] = T[IDX(nx - 2, j)];
+}
+/* part2_utils.jl:21-24 */
+void orc_bc_apply(double *T, int nx, int ny) { orc_bc_dirichlet(T, nx, ny); orc_bc_neumann(T, nx, ny); }
+
+/* multigrid.jl:173-188 */
+void orc_residual2d(const double *restrict u, const double *restrict f, double h, double c,
+                    double *restrict res, int nx, int ny)
+{
+    const double C = 4.0 + c * (h * h);
+    const double _h2 = 1 / (h * h);
+#pragma omp parallel for schedule(static)
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i)
+            res[IDX(i, j)] = ((u[IDX(i + 1, j)] + u[IDX(i - 1, j)] + u[IDX(i, j + 1)] + u[IDX(i, j - 1)] -
+                               C * u[IDX(i, j)]) * _h2 - f[IDX(i, j)]);
+}
+
+/* sum(x.^2) over all entries: per-column partials combined in column order */
+static double sumsq(const double *x, int nx, int ny)
+{
+    double *part = (double *)malloc(ny * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; ++j) {
+        double a = 0.0;
+        for (int i = 0; i < nx; ++i) a += x[IDX(i, j)] * x[IDX(i, j)];
+        part[j] = a;
+    }
+    double t = 0.0;
+    for (int j = 0; j < ny; ++j) t += part[j];
+    free(part);
+    return t;
+}
+static double dot(const double *x, const double *y, int nx, int ny)
+{
+    double *part = (double *)malloc(ny * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; ++j) {
+        double a = 0.0;
+        for (int i = 0; i < nx; ++i) a += x[IDX(i, j)] * y[IDX(i, j)];
+        part[j] = a;
+    }
+    double t = 0.0;
+    for (int j = 0; j < ny; ++j) t += part[j];
+    free(part);
+    return t;
+}
+double orc_sumsq(const double *x, int nx, int ny) { return sumsq(x, nx, ny); }
+
+/* multigrid.jl:245-258, alpha = 4/5 default */
+double orc_jacobi2d(double *u, const double *f, double h, double c, double *res, int nx, int ny, double alpha,
+                    int unfused)
+{
+    orc_residual2d(u, f, h, c, res, nx, ny);
+    double ss;
+    if (unfused) {
+        /* reference structure: res.^2 temporary, then sum */
+        size_t n = (size_t)nx * ny;
+        double *tmp = (double *)malloc(n * sizeof(double));
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < n; ++p) tmp[p] = res[p] * res[p];
+        double *part = (double *)malloc(ny * sizeof(double));
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < ny; ++j) {
+            double a = 0.0;
+            for (int i = 0; i < nx; ++i) a += tmp[IDX(i, j)];
+            part[j] = a;
+        }
+        ss = 0.0;
+        for (int j = 0; j < ny; ++j) ss += part[j];
+        free(part); free(tmp);
+    } else {
+        ss = sumsq(res, nx, ny);
+    }
+    double r_rms = sqrt(ss / ((double)nx * ny));
+    const double w = alpha * ((h * h) / (4.0 + c * (h * h)));
+    size_t n = (size_t)nx * ny;
+#pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < n; ++p) u[p] += w * res[p];
+    return r_rms;
+}
+
+/* multigrid.jl:269-297 (serial lexicographic; alpha = 1) */
+double orc_gs2d_lex(double *u, const double *f, double h, double c, int nx, int ny, double alpha)
+{
+    double r_rms = 0.0;
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i) {
+            double r = (u[IDX(i + 1, j)] + u[IDX(i - 1, j)] + u[IDX(i, j + 1)] + u[IDX(i, j - 1)] -
+                        (4.0 + c * (h * h)) * u[IDX(i, j)]) / (h * h) - f[IDX(i, j)];
+            u[IDX(i, j)] = u[IDX(i, j)] + alpha * ((h * h) / (4.0 + c * (h * h))) * r;
+            r_rms = r_rms + r * r;
+        }
+    return sqrt(r_rms / ((double)nx * ny));
+}
+
+/* Variant B smoother (no reference implementation): red half-sweep ((i+j) even, 0-based) then black,
+ * alpha = 1, r_rms accumulated from the pre-update point residuals like orc_gs2d_lex; arithmetic of the
+ * point update identical to multigrid.jl:279-286. Per-column partial sums combined in column order,
+ * red total first, then black. */
+double orc_rbgs2d(double *u, const double *f, double h, double c, int nx, int ny)
+{
+    const double C = 4.0 + c * (h * h), h2 = h * h, w = 1.0 * (h2 / C);
+    double tot = 0.0;
+    double *part = (double *)malloc(ny * sizeof(double));
+    for (int color = 0; color < 2; ++color) {
+#pragma omp parallel for schedule(static)
+        for (int j = 1; j < ny - 1; ++j) {
+            double a = 0.0;
+            int i0 = 1 + ((1 + j + color) & 1);
+            for (int i = i0; i < nx - 1; i += 2) {
+                double r = (u[IDX(i + 1, j)] + u[IDX(i - 1, j)] + u[IDX(i, j + 1)] + u[IDX(i, j - 1)] -
+                            C * u[IDX(i, j)]) / h2 - f[IDX(i, j)];
+                u[IDX(i, j)] = u[IDX(i, j)] + w * r;
+                a += r * r;
+            }
+            part[j] = a;
+        }
+        double t = 0.0;
+        for (int j = 1; j < ny - 1; ++j) t += part[j];
+        tot += t;
+    }
+    free(part);
+    return sqrt(tot / ((double)nx * ny));
+}
+
+/* multigrid.jl:330-358: zero, inject odd (1-based) fine points 3..n-2, Neumann iff apply_BCs */
+void orc_restrict_inject(const double *fine, double *coarse, int nx, int ny, int apply_BCs)
+{
+    const int nxc = 1 + (nx - 1) / 2, nyc = 1 + (ny - 1) / 2;
+    memset(coarse, 0, (size_t)nxc * nyc * sizeof(double));
+    for (int J = 1; J < nyc - 1; ++J)
+        for (int I = 1; I < nxc - 1; ++I) coarse[(size_t)I + (size_t)nxc * J] = fine[IDX(2 * I, 2 * J)];
+    if (apply_BCs) orc_bc_neumann(coarse, nxc, nyc);
+}
+
+/* Variant B: full weighting [1 2 1; 2 4 2; 1 2 1]/16 on interior coarse points. Fixed evaluation order:
+ * ((corners sum) + 2*(edges sum) + 4*centre) * (1/16) with corners (SW+SE)+(NW+NE), edges (W+E)+(S+N). */
+void orc_restrict_fw(const double *fine, double *coarse, int nx, int ny, int apply_BCs)
+{
+    const int nxc = 1 + (nx - 1) / 2, nyc = 1 + (ny - 1) / 2;
+    memset(coarse, 0, (size_t)nxc * nyc * sizeof(double));
+    for (int J = 1; J < nyc - 1; ++J)
+        for (int I = 1; I < nxc - 1; ++I) {
+            int i = 2 * I, j = 2 * J;
+            double corners = (fine[IDX(i - 1, j - 1)] + fine[IDX(i + 1, j - 1)]) +
+                             (fine[IDX(i - 1, j + 1)] + fine[IDX(i + 1, j + 1)]);
+            double edges = (fine[IDX(i - 1, j)] + fine[IDX(i + 1, j)]) + (fine[IDX(i, j - 1)] + fine[IDX(i, j + 1)]);
+            coarse[(size_t)I + (size_t)nxc * J] = ((corners + 2.0 * edges) + 4.0 * fine[IDX(i, j)]) * 0.0625;
+        }
+    if (apply_BCs) orc_bc_neumann(coarse, nxc, nyc);
+}
+
+/* multigrid.jl:365-396 (serial loop order = the CPU arrival order of the scatter): j outer, i inner */
+void orc_prolongate(const double *coarse, double *fine, int nx, int ny, int apply_BCs)
+{
+    const double a2 = 1.0 / 2.0, a4 = 1.0 / 4.0;
+    const int nxc = 1 + (nx - 1) / 2;
+    memset(fine, 0, (size_t)nx * ny * sizeof(double));
+    for (int j = 2; j <= ny - 3; j += 2)
+        for (int i = 2; i <= nx - 3; i += 2) {
+            double v = coarse[(size_t)(i / 2) + (size_t)nxc * (j / 2)];
+            fine[IDX(i, j)] = fine[IDX(i, j)] + v; /* parallel variants add; fine is 0 here so identical */
+            fine[IDX(i + 1, j)] = fine[IDX(i + 1, j)] + a2 * v;
+            fine[IDX(i - 1, j)] = fine[IDX(i - 1, j)] + a2 * v;
+            fine[IDX(i, j + 1)] = fine[IDX(i, j + 1)] + a2 * v;
+            fine[IDX(i, j - 1)] = fine[IDX(i, j - 1)] + a2 * v;
+            fine[IDX(i + 1, j + 1)] = fine[IDX(i + 1, j + 1)] + a4 * v;
+            fine[IDX(i + 1, j - 1)] = fine[IDX(i + 1, j - 1)] + a4 * v;
+            fine[IDX(i - 1, j + 1)] = fine[IDX(i - 1, j + 1)] + a4 * v;
+            fine[IDX(i - 1, j - 1)] = fine[IDX(i - 1, j - 1)] + a4 * v;
+        }
+    if (apply_BCs) orc_bc_neumann(fine, nx, ny);
+}
+
+/* krylov.jl:7-13 */
+void orc_matvec2d(const double *restrict T, double hx, double hy, double c, double *restrict out, int nx, int ny)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i)
+            out[IDX(i, j)] = ((T[IDX(i + 1, j)] - 2 * T[IDX(i, j)] + T[IDX(i - 1, j)]) / (hx * hx) +
+                              (T[IDX(i, j + 1)] - 2 * T[IDX(i, j)] + T[IDX(i, j - 1)]) / (hy * hy)) -
+                             c * T[IDX(i, j)];
+}
+
+/* krylov.jl:55-91. Returns res_rms; *iters_out = iterations performed. */
+double orc_cg2d(double *x_in, const double *b, double hx, double hy, double c, double tol, int Nmax, int nx, int ny,
+                int *iters_out)
+{
+    size_t n = (size_t)nx * ny;
+    double normb = sqrt(sumsq(b, nx, ny));
+    double tolb = tol * normb;
+    double *r = (double *)malloc(n * sizeof(double)), *p = (double *)malloc(n * sizeof(double));
+    double *ph = (double *)malloc(n * sizeof(double)), *x = (double *)calloc(n, sizeof(double));
+    memcpy(r, b, n * sizeof(double)); memcpy(p, b, n * sizeof(double)); memcpy(ph, b, n * sizeof(double));
+    double rho = dot(r, r, nx, ny);
+    int it = 0;
+    for (int i = 1; i <= Nmax; ++i) {
+        it = i;
+        orc_matvec2d(p, hx, hy, c, ph, nx, ny);
+        double alpha = rho / dot(p, ph, nx, ny);
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < n; ++q) x[q] += alpha * p[q];
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < n; ++q) r[q] -= alpha * ph[q];
+        double normr = sqrt(sumsq(r, nx, ny));
+        if (normr < tolb) break;
+        double rho_old = rho;
+        rho = dot(r, r, nx, ny);
+        double beta = rho / rho_old;
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < n; ++q) p[q] = r[q] + beta * p[q];
+    }
+    memcpy(x_in, x, n * sizeof(double));
+    double out = sqrt(sumsq(r, nx, ny) / ((double)nx * ny));
+    free(r); free(p); free(ph); free(x);
+    if (iters_out) *iters_out = it;
+    return out;
+}
+
+static double smooth(double *u, const double *f, double h, double c, double *res, int nx, int ny, const orc_mg_opt *o)
+{
+    if (o->smoother == ORC_SMOOTH_RBGS) return orc_rbgs2d(u, f, h, c, nx, ny);
+    return orc_jacobi2d(u, f, h, c, res, nx, ny, 4.0 / 5.0, o->unfused);
+}
+
+/* multigrid.jl:91-170. Returns res_rms, or NAN on "not a power of 2" (multigrid.jl:95-97). */
+double orc_vcycle2d(double *u_f, const double *rhs, double h, double c, double tol, int nx, int ny, int apply_BCs,
+                    const orc_mg_opt *o)
+{
+    if (((nx - 1) & 1) || ((ny - 1) & 1)) return NAN;
+    const int nxc = 1 + (nx - 1) / 2, nyc = 1 + (ny - 1) / 2;
+    size_t nf = (size_t)nx * ny, nc = (size_t)nxc * nyc;
+    double *res_f = (double *)calloc(nf, sizeof(double));
+    double *corr_f = (double *)calloc(nf, sizeof(double));
+    double *corr_c = (double *)calloc(nc, sizeof(double));
+    double *res_c = (double *)calloc(nc, sizeof(double));
+    double res_rms = 0.0;
+    int mn = nx < ny ? nx : ny;
+    if (mn > o->coarse_solve_size) {
+        res_rms = smooth(u_f, rhs, h, c, res_f, nx, ny, o);
+        res_rms = smooth(u_f, rhs, h, c, res_f, nx, ny, o);
+        orc_residual2d(u_f, rhs, h, c, res_f, nx, ny);
+        if (o->restriction == ORC_RESTRICT_FW) orc_restrict_fw(res_f, res_c, nx, ny, apply_BCs);
+        else orc_restrict_inject(res_f, res_c, nx, ny, apply_BCs);
+        memset(corr_c, 0, nc * sizeof(double));
+        res_rms = orc_vcycle2d(corr_c, res_c, h * 2, c, tol, nxc, nyc, apply_BCs, o);
+        orc_prolongate(corr_c, corr_f, nx, ny, apply_BCs);
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < nf; ++p) u_f[p] = u_f[p] - corr_f[p];
+        res_rms = smooth(u_f, rhs, h, c, res_f, nx, ny, o);
+        res_rms = smooth(u_f, rhs, h, c, res_f, nx, ny, o);
+    } else {
+        int iters = 20 * o->coarse_solve_size;
+        if (o->coarse_solver == ORC_COARSE_JACOBI) {
+            double tol_rhs = tol * sqrt(sumsq(rhs, nx, ny) / ((double)nx * ny));
+            long sweeps = 0;
+            for (int i = 1; i <= iters; ++i) {
+                res_rms = smooth(u_f, rhs, h, c, res_f, nx, ny, o);
+                ++sweeps;
+                if (res_rms < tol_rhs) break;
+            }
+            g_coarse_sweeps_last = sweeps;
+        } else {
+            int it = 0;
+            res_rms = orc_cg2d(u_f, rhs, h, h, c, tol, iters, nx, ny, &it);
+            g_coarse_sweeps_last = it;
+        }
+    }
+    free(res_f); free(corr_f); free(corr_c); free(res_c);
+    return res_rms;
+}
+
+/* multigrid.jl:41-84. Returns r_rms; *ncycles = V-cycles executed; rel_hist (nullable, niters) = r_rms/f_rms.
+ * Returns NAN for the reference's error conditions (asserts :45-46, error :96). */
+double orc_mgsolve2d(double *u, const double *f, double h, double c, double tol, int niters, int apply_BCs, int nx,
+                     int ny, const orc_mg_opt *o, int *ncycles, double *rel_hist)
+{
+    int mn = nx < ny ? nx : ny;
+    int cs1 = o->coarse_solve_size - 1;
+    if (o->coarse_solve_size > mn || cs1 <= 0 || (cs1 & (cs1 - 1))) return NAN;
+    double f_rms = sqrt(sumsq(f, nx, ny) / ((double)nx * ny));
+    double tolf = tol * f_rms;
+    double r_rms = 0.0;
+    int n = 0;
+    for (int iter = 1; iter <= niters; ++iter) {
+        if (apply_BCs) orc_bc_apply(u, nx, ny);
+        r_rms = orc_vcycle2d(u, f, h, c, tol, nx, ny, apply_BCs, o);
+        n = iter;
+        if (rel_hist) rel_hist[iter - 1] = r_rms / f_rms;
+        if (isnan(r_rms)) break;
+        if (r_rms < tolf) break;
+    }
+    if (ncycles) *ncycles = n;
+    return r_rms;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Navier-Stokes step (part2.jl:181-250)                                      */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    double k, Ra, Pr;
+    int nx, ny;
+    double ttot, beta;
+    int niters;
+    double tol, a_dif, a_adv;
+} orc_ns_params; /* SimIn_t part2.jl:30-46 minus the init strategies */
+
+/* part2.jl:58-63 cosine branch */
+void orc_ns_init_cosine(double *M, int nx, int ny)
+{
+    double h = 1.0 / (ny - 1.0), width = (nx - 1.0) / (ny - 1.0);
+    for (int i = 0; i < nx; ++i) {
+        double v = 0.5 * (1.0 + cos((3.0 * M_PI * (double)i * h) / width));
+        for (int j = 0; j < ny; ++j) M[IDX(i, j)] = v;
+    }
+}
+
+typedef struct {
+    double dt;
+    int cycles_S, cycles_T, cycles_W;
+    double r_S, r_T, r_W;
+} orc_ns_stepinfo;
+
+/* One time step. Work arrays are allocated inside (oracle: clarity over speed).
+ * out_aux (nullable): 7 arrays nx*ny each: vx, vy, v, Ra_dTdx, dT2, dW2, (unused) */
+void orc_ns_step(const orc_ns_params *P, const orc_mg_opt *o, double *S, double *T, double *W,
+                 orc_ns_stepinfo *info, double *out_aux)
+{
+    const int nx = P->nx, ny = P->ny;
+    size_t n = (size_t)nx * ny;
+    const double h = 1.0 / (ny - 1.0), hx = h, hy = h;
+    const double dt_dif = (P->a_dif * (h * h)) / fmax(P->k, P->Pr);
+    double *vx = (double *)calloc(n, 8), *vy = (double *)calloc(n, 8), *v = (double *)calloc(n, 8);
+    double *dT2 = (double *)calloc(n, 8), *dTx = (double *)calloc(n, 8), *dTy = (double *)calloc(n, 8);
+    double *dW2 = (double *)calloc(n, 8), *dWx = (double *)calloc(n, 8), *dWy = (double *)calloc(n, 8);
+    double *Ra_dTdx = (double *)calloc(n, 8), *rhs = (double *)calloc(n, 8);
+
+    info->r_S = orc_mgsolve2d(S, W, h, 0.0, P->tol, P->niters, 0, nx, ny, o, &info->cycles_S, NULL);
+    /* part2.jl:90-96 */
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i) {
+            vx[IDX(i, j)] = (S[IDX(i, j + 1)] - S[IDX(i, j - 1)]) / (2 * hy);
+            vy[IDX(i, j)] = -(S[IDX(i + 1, j)] - S[IDX(i - 1, j)]) / (2 * hx);
+        }
+    double vmax = 0.0, vxmax = 0.0, vymax = 0.0;
+    for (size_t p = 0; p < n; ++p) {
+        v[p] = sqrt(vx[p] * vx[p] + vy[p] * vy[p]);
+        if (v[p] > vmax) vmax = v[p];
+        if (fabs(vx[p]) > vxmax) vxmax = fabs(vx[p]);
+        if (fabs(vy[p]) > vymax) vymax = fabs(vy[p]);
+    }
+    /* part2.jl:76-87 */
+    double dt;
+    if (vmax == 0) dt = dt_dif;
+    else {
+        double dt_adv = P->a_adv * fmin(h / vxmax, h / vymax);
+        dt = (P->beta >= 0.5 ? dt_adv : fmin(dt_dif, dt_adv));
+    }
+    info->dt = dt;
+    orc_bc_apply(T, nx, ny);
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i)
+            Ra_dTdx[IDX(i, j)] = P->Ra * (T[IDX(i + 1, j)] - T[IDX(i - 1, j)]) / (2 * hx);
+    /* isapprox(beta, 1.0): |beta-1| <= sqrt(eps) * max(|beta|,1) */
+    int beta_is_one = fabs(P->beta - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(P->beta), 1.0);
+    if (!beta_is_one) {
+        for (int j = 1; j < ny - 1; ++j)
+            for (int i = 1; i < nx - 1; ++i) {
+                dT2[IDX(i, j)] = P->k * ((T[IDX(i + 1, j)] - 2 * T[IDX(i, j)] + T[IDX(i - 1, j)]) / (hx * hx) +
+                                         (T[IDX(i, j + 1)] - 2 * T[IDX(i, j)] + T[IDX(i, j - 1)]) / (hy * hy));
+                dW2[IDX(i, j)] = P->Pr * ((W[IDX(i + 1, j)] - 2 * W[IDX(i, j)] + W[IDX(i - 1, j)]) / (hx * hx) +
+                                          (W[IDX(i, j + 1)] - 2 * W[IDX(i, j)] + W[IDX(i, j - 1)]) / (hy * hy));
+            }
+    }
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i) {
+            size_t p = IDX(i, j);
+            dTx[p] = vx[p] > 0 ? vx[p] * (T[p] - T[IDX(i - 1, j)]) / hx : vx[p] * (T[IDX(i + 1, j)] - T[p]) / hx;
+            dTy[p] = vy[p] > 0 ? vy[p] * (T[p] - T[IDX(i, j - 1)]) / hy : vy[p] * (T[IDX(i, j + 1)] - T[p]) / hy;
+            dWx[p] = vx[p] > 0 ? vx[p] * (W[p] - W[IDX(i - 1, j)]) / hx : vx[p] * (W[IDX(i + 1, j)] - W[p]) / hx;
+            dWy[p] = vy[p] > 0 ? vy[p] * (W[p] - W[IDX(i, j - 1)]) / hy : vy[p] * (W[IDX(i, j + 1)] - W[p]) / hy;
+        }
+    info->cycles_T = info->cycles_W = 0; info->r_T = info->r_W = 0.0;
+    if (P->beta > 0.0) {
+        double c = 1.0 / (P->beta * dt);
+        for (size_t p = 0; p < n; ++p) rhs[p] = -c * (T[p] + dt * (((1.0 - P->beta) * dT2[p] - dTx[p]) - dTy[p]));
+        info->r_T = orc_mgsolve2d(T, rhs, h, c, P->tol, P->niters, 1, nx, ny, o, &info->cycles_T, NULL);
+        c = c / P->Pr;
+        for (size_t p = 0; p < n; ++p)
+            rhs[p] = -c * (W[p] + dt * ((((1.0 - P->beta) * dW2[p] - dWx[p]) - dWy[p]) - P->Pr * Ra_dTdx[p]));
+        info->r_W = orc_mgsolve2d(W, rhs, h, c, P->tol, P->niters, 0, nx, ny, o, &info->cycles_W, NULL);
+    } else {
+        for (size_t p = 0; p < n; ++p) T[p] = T[p] + dt * ((dT2[p] - dTx[p]) - dTy[p]);
+        for (size_t p = 0; p < n; ++p) W[p] = W[p] + dt * (((dW2[p] - dWx[p]) - dWy[p]) - P->Pr * Ra_dTdx[p]);
+    }
+    if (out_aux) {
+        memcpy(out_aux + 0 * n, vx, n * 8); memcpy(out_aux + 1 * n, vy, n * 8); memcpy(out_aux + 2 * n, v, n * 8);
+        memcpy(out_aux + 3 * n, Ra_dTdx, n * 8); memcpy(out_aux + 4 * n, dT2, n * 8);
+        memcpy(out_aux + 5 * n, dW2, n * 8);
+    }
+    free(vx); free(vy); free(v); free(dT2); free(dTx); free(dTy); free(dW2); free(dWx); free(dWy);
+    free(Ra_dTdx); free(rhs);
+}
