@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native stencil library (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): 3-D pseudo-transient diffusion T_eff in GB/s, 512^3 Float64 per GPU (config #3 at N=1,
+config #5 weak scaling at N>1: z-slabs, dims=(1,1,N), scale_physical_size, reference lag-2 halo semantics).
+  T_eff = 24 B x (nx-2)(ny-2)(nz-2) x PT iterations x N / time      (read Htau, read Ht, write Htau2)
+A "step" is one batch of --iters PT iterations of the device-resident loop (fused flux/residual/update kernel with
+the norm, the exit bookkeeping and the halo push fused in). `value` is timed with the fields resident in HBM;
+`e2e` times the same step through the public host API with the state uploaded from / downloaded to pinned host
+memory inside the timed region. The 2-D multigrid V-cycle numbers (config #2) ride along under "mg".
+
+--impl reference times the reference's CPU algorithm (the OpenMP oracle restating its Threads path, un-fused norm)
+on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_CELL = 24.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="local grid points per side (per GPU)")
+    ap.add_argument("--iters", type=int, default=200, help="PT iterations per step")
+    ap.add_argument("--variant", default="auto", choices=["auto", "tma", "direct"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mg", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(n, seconds, threads=None):
+    """The reference's CPU path (oracle port, un-fused norm like part1_kernel_programming.jl:191) on a bounded sample:
+    as many PT iterations of the same n^3 workload as fit in `seconds`."""
+    from oracle import oracle_lib as O
+    O.build()
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    o = O.Diffusion3D(n, n, n, unfused_norm=True)
+    o.iterate(1)  # warm-up / page touch
+    t0 = time.perf_counter()
+    o.iterate(1)
+    t1 = time.perf_counter() - t0
+    iters = max(2, min(200, int(seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    o.iterate(iters)
+    dt = time.perf_counter() - t0
+    cells = float(n - 2) ** 3
+    return {"value": BYTES_PER_CELL * cells * iters / dt / 1e9, "unit": "GB/s", "cores": O.num_threads(),
+            "kind": "port", "ms_per_iteration": dt / iters * 1e3,
+            "sample": f"{iters} PT iterations of the {n}^3 Float64 grid (un-fused norm passes like the reference), "
+                      f"OpenMP oracle port of the reference's Threads path, {O.num_threads()} threads"}, iters, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.n
+    per_step_budget = max(2.0, min(30.0, 90.0 / max(1, args.steps + args.warmup)))
+    from oracle import oracle_lib as O
+    O.build()
+    o = O.Diffusion3D(n, n, n, unfused_norm=True)
+    o.iterate(1)
+    t0 = time.perf_counter(); o.iterate(1); t1 = time.perf_counter() - t0
+    iters = max(1, min(args.iters, int(per_step_budget / max(t1, 1e-6))))
+    for _ in range(args.warmup):
+        o.iterate(iters)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.iterate(iters)
+    dt = time.perf_counter() - t0
+    cells = float(n - 2) ** 3
+    val = BYTES_PER_CELL * cells * iters * args.steps / dt / 1e9
+    sample = (f"{iters} PT iterations per step of the {n}^3 Float64 grid on the host CPU (OpenMP oracle port of the "
+              f"reference's Threads path, un-fused norm), {O.num_threads()} threads")
+    out = {"impl": "reference", "metric": "diffusion3d_T_eff", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"3D pseudo-transient diffusion {n}^3 Float64 (part1_benchmark.jl shape), "
+                                  f"{iters} PT iterations per step", "iters_per_step": iters},
+           "cpu_baseline": {"value": val, "unit": "GB/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def mg_bench(device, peak):
+    """Config #2: 2-D multigrid V-cycle, 1025^2 (the "1023^2" config) -- DoF/s per V-cycle, device-resident."""
+    try:
+        from b200stencil import part2
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    try:
+        return part2.bench_vcycle(device=device, hbm_peak_gbs=peak)
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import b200stencil  # noqa: F401
+    from b200stencil import capi, part1
+
+    if not torch.cuda.is_available() or capi.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N = world
+    if args.gpus != N and rank == 0:
+        print(f"[bench] --gpus {args.gpus} but WORLD_SIZE {N}: using {N}", file=sys.stderr)
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    n = args.n
+    kv = {"auto": capi.KERNEL_AUTO, "tma": capi.KERNEL_TMA, "direct": capi.KERNEL_DIRECT}[args.variant]
+
+    s = part1.Diffusion3D(n, n, n, nslabs=N, devices=[dev], slab_begin=rank, slab_count=1 if N > 1 else None,
+                          halo_mode=capi.HALO_REFERENCE_LAG2, scale_physical_size=(N > 1), kernel_variant=kv)
+    s.init_gaussian()
+    if N > 1:
+        blobs = [None] * N
+        dist.all_gather_object(blobs, s.ipc_export())
+        s.ipc_connect(blobs)
+        dist.barrier()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cells = float(n - 2) ** 3
+    iters = args.iters
+    # ---- device-resident measurement ------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        s.iterate(iters, want_hist=False)
+    sampler = ClockSampler(dev)
+    launches0, _ = s.stats()
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        s.iterate(iters, want_hist=False)
+        dev_ms += s.stats()[1]  # CUDA events on the launching stream, inside the library
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches1, _ = s.stats()
+    dev_ms = max_over_ranks(dev_ms)
+    wall = max_over_ranks(wall)
+    value = BYTES_PER_CELL * cells * iters * args.steps * N / (dev_ms * 1e-3) / 1e9
+    ms_per_step = dev_ms / args.steps
+    kern_ms = dev_ms / (args.steps * iters)
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_CELL * cells / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "step_tma_kernel (fused flux/residual/update + norm + exit test)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells,
+                "avg_launch_ms": kern_ms}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("diffusion3d_step_512_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the host API: pinned host state in, state out, every step ---------------------------
+    nbytes = n * n * n * 8
+    e2e = None
+    if args.no_e2e:
+        s.close()
+    else:
+        e2e = _e2e(args, s, n, N, cells, iters, torch, sync_all, max_over_ranks, nbytes)
+    mg = None
+    cpu = None
+    _finish(args, rank, N, n, dev, peak, value, ms_per_step, wall, roofline, e2e, launches1 - launches0, clocks, iters,
+            mg, cpu, dist)
+
+
+def _e2e(args, s, n, N, cells, iters, torch, sync_all, max_over_ranks, nbytes):
+    host_in = torch.empty(n * n * n, dtype=torch.float64).pin_memory()
+    host_out = torch.empty(n * n * n, dtype=torch.float64).pin_memory()
+    s.download_state(host_in)  # a physically meaningful state to start every e2e step from
+    for _ in range(2):
+        s.upload_state(host_in); s.iterate(iters, want_hist=False); s.download_state(host_out)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.upload_state(host_in)
+        s.iterate(iters, want_hist=False)
+        s.download_state(host_out)
+    sync_all()
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": BYTES_PER_CELL * cells * iters * args.steps * N / e2e_wall / 1e9, "unit": "GB/s",
+           "h2d_bytes_per_step": nbytes * N, "d2h_bytes_per_step": nbytes * N,
+           "ms_per_step": e2e_wall / args.steps * 1e3, "checksum": float(host_out[:: 4097].sum())}
+    s.close()
+    return e2e
+
+
+def _finish(args, rank, N, n, dev, peak, value, ms_per_step, wall, roofline, e2e, nlaunch, clocks, iters, mg, cpu, dist):
+    if rank == 0:
+        if not args.no_mg and N == 1:
+            mg = mg_bench(dev, peak)
+        if not args.no_cpu_baseline and N == 1:
+            try:
+                cpu, _, _ = cpu_reference_run(n, args.cpu_seconds)
+            except Exception as e:  # pragma: no cover
+                cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        out = {"metric": "diffusion3d_T_eff", "value": value, "unit": "GB/s", "n_gpus": N, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"3D pseudo-transient diffusion {n}^3 Float64 per GPU (part1_benchmark.jl shape; "
+                                      f"BASELINE configs[2]{' / configs[4] weak scaling, z-slabs' if N > 1 else ''}), "
+                                      f"{iters} PT iterations per step, Gaussian initial condition",
+                          "iters_per_step": iters, "local_grid": [n, n, n], "dims": [1, 1, N],
+                          "halo_mode": "reference_lag2", "l2": "inputs (3 GiB of fields per GPU) larger than L2",
+                          "kernel_variant": args.variant, "timing": "CUDA events inside the library on its stream, "
+                          "max over ranks; wall-clock cross-check in wall_ms_per_step"},
+               "wall_ms_per_step": wall / args.steps * 1e3,
+               "roofline": roofline, "e2e": e2e, "gpu_launches": int(nlaunch), "clocks": clocks}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        if mg is not None:
+            out["mg"] = mg
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

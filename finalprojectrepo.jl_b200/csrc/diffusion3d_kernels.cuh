@@ -1,0 +1,333 @@
+// diffusion3d_kernels.cuh -- device code of hot path 1: the fused flux/residual/update step of the 3-D dual-time
+// (pseudo-transient) diffusion solver, with the residual norm, the PT-loop exit test and the z-slab halo exchange
+// fused in.
+//
+// Reference semantics (file:line relative to the reference repository):
+//   scripts-part1/part1_kernel_programming.jl:12-20   @qx/@qy/@qz      q(i) = -D_d * (H[i] - H[i-1])
+//   scripts-part1/part1_kernel_programming.jl:46-58   diffusion_3D_step_tau (and the shared-memory twin :75-97)
+//   scripts-part1/part1_kernel_programming.jl:177-193 while err > tol && iter < iter_max ... update_halo!(Htau); swap
+//   scripts-part1/part1_utils.jl:36-40                dist_norm_L2
+// Arithmetic is evaluated in exactly the order written there and this translation unit is compiled with
+// -fmad=false, so single-GPU fields are bit-identical to a non-contracting CPU evaluation.
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+// Device-resident state of the PT loop of one time step (one copy per device that hosts slabs of a handle).
+struct PTState {
+    int it;          // iter_inner of the current time step
+    int done;        // exit flag: kernels launched after it is set return immediately
+    int iter_max;    // part1_kernel_programming.jl:130
+    int check;       // 1: evaluate "err > tol" (solve_timestep); 0: fixed count (iterate)
+    int error;       // 1: cross-GPU wait timed out
+    int hist_pos;    // next entry of err_hist
+    int hist_cap;
+    int pad;
+    double tol;
+    double err;
+    double sumsq;          // global sum over ranks and cells of (R*dt)^2
+    double sqrt_total_N;   // sqrt(prod(dims)*nx*ny*nz), part1_kernel_programming.jl:124,191
+    long long total_iters; // PT iterations since create (selects the ping-pong parity)
+    unsigned long long seq; // cross-GPU sequence number of the next partial to publish / consume
+};
+
+constexpr int kMaxRanks = 64;
+
+// Cross-GPU (one process per GPU) reduction mailbox living in every rank's arena: peers store their partial and then
+// the sequence number. Two generations (seq parity) so a fast peer never overwrites an unread value.
+struct RankSlots {
+    double value[2][kMaxRanks];
+    unsigned long long seq[2][kMaxRanks];
+};
+
+struct StepParams {
+    const double *Ht;
+    const double *A;  // Htau  (read)
+    double *B;        // Htau2 (written, interior only)
+    double *R;        // dHdtau, nullable
+    int nx, ny, nz;
+    double dtau, _dt, _dx, _dy, _dz, mD_dx, mD_dy, mD_dz;  // mD_* = -D_d*
+    double norm_scale;                                     // dt in "residual_H * dt"
+    double *partials;                                      // one per block
+    unsigned int *ticket;
+    double *sumsq_out;   // nullable: receives the local sum
+    PTState *state;      // nullable (L0 call)
+    double *err_hist;    // nullable
+    int fuse_finalize;   // 1: single slab -> the last block runs the exit test itself
+    // z-slab halo exchange fused into the kernel. Pointers to the first element of the neighbour's
+    // halo plane of the buffer with the same parity as B (peer-mapped when the neighbour is on another GPU).
+    double *push_lo;     // low neighbour's plane nz-1, nullable
+    double *push_hi;     // high neighbour's plane 0, nullable
+    int consistent;      // 0: reference lag-2 semantics (forward the OLD content of B's boundary planes);
+                         // 1: forward the values just computed
+    // one-process-per-GPU mode: publish the local sum to every rank's RankSlots
+    RankSlots *const *peer_slots;  // device array [nranks] of (peer-mapped) pointers, nullable
+    int nranks, myrank;
+    int zchunk;          // interior planes per block
+};
+
+__device__ __forceinline__ void pt_finalize(PTState *s, double total, double *err_hist)
+{
+    // err = dist_norm_L2(residual_H*dt)/sqrt(total_N)   part1_kernel_programming.jl:191
+    const double err = sqrt(total) / s->sqrt_total_N;
+    const int it = s->it + 1;
+    s->it = it;
+    s->err = err;
+    s->sumsq = total;
+    s->total_iters += 1;
+    if (err_hist != nullptr && s->hist_pos < s->hist_cap) err_hist[s->hist_pos++] = err;
+    // while err > tol && iter_inner < iter_max        part1_kernel_programming.jl:179
+    const bool go_on = s->check ? (err > s->tol && it < s->iter_max) : (it < s->iter_max);
+    if (!go_on) s->done = 1;
+}
+
+// Residual of one cell, operation order of part1_kernel_programming.jl:48-53.
+__device__ __forceinline__ double cell_residual(double c, double xl, double xr, double ys, double yn, double zp, double zn,
+                                                double ht, const StepParams &p)
+{
+    return ((p.mD_dx * (xr - c)) - (p.mD_dx * (c - xl))) * p._dx + ((p.mD_dy * (yn - c)) - (p.mD_dy * (c - ys))) * p._dy +
+           ((p.mD_dz * (zn - c)) - (p.mD_dz * (c - zp))) * p._dz + (c - ht) * p._dt;
+}
+
+// Shared tail of both kernel variants: block partial -> deterministic grid sum -> (optionally) exit test / publish.
+__device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, double *red)
+{
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const int bl = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    double bsum = block_sum(acc, red);
+    double total = 0.0;
+    if (grid_sum_last_block(bsum, p.partials, p.ticket, nblocks, bl, red, &total)) {
+        if (p.sumsq_out != nullptr) *p.sumsq_out = total;
+        if (p.peer_slots != nullptr) {
+            const unsigned long long seq = p.state->seq;
+            const int g = (int)(seq & 1ull);
+            for (int r = 0; r < p.nranks; ++r) p.peer_slots[r]->value[g][p.myrank] = total;
+            __threadfence_system();
+            for (int r = 0; r < p.nranks; ++r) st_release_sys_u64(&p.peer_slots[r]->seq[g][p.myrank], seq);
+        } else if (p.fuse_finalize) {
+            pt_finalize(p.state, total, p.err_hist);
+        }
+    }
+    (void)tid;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Variant DIRECT: one thread per (x,y) column, z-marching with a register queue for the z neighbours; x/y neighbours
+// come through L1/L2. Works for every size and alignment; the correctness anchor and the small-grid path.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDirBX = 64, kDirBY = 4;
+
+__global__ void __launch_bounds__(kDirBX *kDirBY) step_direct_kernel(const StepParams p)
+{
+    __shared__ double red[32];
+    if (p.state != nullptr && p.state->done) return;
+    const int x = blockIdx.x * kDirBX + threadIdx.x;
+    const int y = blockIdx.y * kDirBY + threadIdx.y;
+    const int zs = 1 + blockIdx.z * p.zchunk;
+    const int ze = min(zs + p.zchunk, p.nz - 1);
+    const bool inb = x < p.nx && y < p.ny;
+    const bool valid = x >= 1 && x <= p.nx - 2 && y >= 1 && y <= p.ny - 2;
+    const size_t sy = (size_t)p.nx, sz = (size_t)p.nx * p.ny;
+    double acc = 0.0;
+    if (inb) {
+        size_t q = (size_t)x + sy * y + sz * zs;
+        double zp = 0.0, c = 0.0;
+        if (valid) { zp = p.A[q - sz]; c = p.A[q]; }
+        for (int z = zs; z < ze; ++z, q += sz) {
+            const bool plo = p.push_lo != nullptr && z == 1;
+            const bool phi = p.push_hi != nullptr && z == p.nz - 2;
+            double outv = 0.0;
+            if (plo || phi) outv = p.B[q];  // old content (also the value forwarded for boundary cells)
+            if (valid) {
+                const double zn = p.A[q + sz];
+                const double r = cell_residual(c, p.A[q - 1], p.A[q + 1], p.A[q - sy], p.A[q + sy], zp, zn, p.Ht[q], p);
+                const double b = c - p.dtau * r;
+                p.B[q] = b;
+                if (p.R != nullptr) p.R[q] = r;
+                const double v = r * p.norm_scale;
+                acc += v * v;
+                if (p.consistent) outv = b;
+                zp = c;
+                c = zn;
+            }
+            if (plo) p.push_lo[(size_t)x + sy * y] = outv;
+            if (phi) p.push_hi[(size_t)x + sy * y] = outv;
+        }
+        if (p.push_lo != nullptr || p.push_hi != nullptr) __threadfence_system();
+    }
+    step_epilogue(p, acc, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Variant TMA: 2.5-D z-marching. A block owns an (TX x TY) xy-tile and a chunk of z planes. Planes of Htau (with a
+// one-cell y halo and a two-cell, 16-byte aligned x halo) and of Ht are staged into a ring of S shared-memory stages
+// by TMA (cp.async.bulk.tensor.3d, completion on an mbarrier per stage; out-of-range parts of a box are zero-filled
+// by the hardware and masked in the arithmetic). Every thread owns two x-adjacent cells: the z neighbours live in a
+// register queue, x/y neighbours are read from the staged plane, the result goes out as one coalesced 16-byte store.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TX, int TY>
+struct TmaCfg {
+    static constexpr int BW = TX + 4;  // box width: cells X0-2 .. X0+TX+1
+    static constexpr int BH = TY + 2;  // rows Y0-1 .. Y0+TY
+    static constexpr int A_BYTES = BW * BH * 8;
+    static constexpr int H_BYTES = TX * TY * 8;
+    static constexpr int A_STRIDE = ((A_BYTES + 127) / 128) * 128 / 8;  // doubles, 128-byte aligned stages
+    static constexpr int H_STRIDE = ((H_BYTES + 127) / 128) * 128 / 8;
+    static constexpr int THREADS = (TX / 2) * TY;
+    static constexpr size_t smem_bytes(int S) { return (size_t)S * (A_STRIDE + H_STRIDE) * 8 + (size_t)S * 8 + 128; }
+};
+
+template <int TX, int TY, int S>
+__global__ void __launch_bounds__((TX / 2) * TY)
+    step_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapHt, const StepParams p)
+{
+    using C = TmaCfg<TX, TY>;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ double red[32];
+    if (p.state != nullptr && p.state->done) return;
+
+    // 128-byte aligned carve-up of the dynamic shared memory
+    unsigned char *base = (unsigned char *)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+    double *sA = (double *)base;
+    double *sH = sA + (size_t)S * C::A_STRIDE;
+    uint64_t *full = (uint64_t *)(sH + (size_t)S * C::H_STRIDE);
+
+    const int tid = threadIdx.x + (TX / 2) * threadIdx.y;
+    const int X0 = blockIdx.x * TX, Y0 = blockIdx.y * TY;
+    const int zs = 1 + blockIdx.z * p.zchunk;
+    const int ze = min(zs + p.zchunk, p.nz - 1);
+    const int nplanes = (ze - zs) + 2;  // planes zs-1 .. ze
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto issue = [&](int q) {
+        const int st = q % S;
+        const int z = zs - 1 + q;
+        const bool needH = (q >= 1 && q <= nplanes - 2);
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(C::A_BYTES + (needH ? C::H_BYTES : 0)));
+        tma_load_3d(sA + (size_t)st * C::A_STRIDE, &mapA, &full[st], X0 - 2, Y0 - 1, z);
+        if (needH) tma_load_3d(sH + (size_t)st * C::H_STRIDE, &mapHt, &full[st], X0, Y0, z);
+    };
+    if (tid == 0) {
+        const int n0 = nplanes < S ? nplanes : S;
+        for (int q = 0; q < n0; ++q) issue(q);
+    }
+
+    const int x = X0 + 2 * (int)threadIdx.x, y = Y0 + (int)threadIdx.y;
+    const bool yok = y >= 1 && y <= p.ny - 2;
+    const bool valid0 = yok && x >= 1 && x <= p.nx - 2;
+    const bool valid1 = yok && x + 1 <= p.nx - 2;  // x+1 >= 1 always
+    const bool inb0 = x < p.nx && y < p.ny, inb1 = x + 1 < p.nx && y < p.ny;
+    const int ci = ((int)threadIdx.y + 1) * C::BW + 2 * (int)threadIdx.x + 2;  // centre pair inside a staged plane
+    const int hi = (int)threadIdx.y * TX + 2 * (int)threadIdx.x;
+    const size_t sy = (size_t)p.nx, sz = (size_t)p.nx * p.ny;
+    const size_t pxy = (size_t)x + sy * y;
+
+    double acc = 0.0;
+    // plane zs-1: only its centre values are needed
+    mbar_wait(&full[0], 0);
+    double2 aprev = *reinterpret_cast<const double2 *>(sA + ci);
+    __syncthreads();
+    if (tid == 0 && S < nplanes) issue(S);
+    mbar_wait(&full[1 % S], (uint32_t)((1 / S) & 1));
+    double2 acur = *reinterpret_cast<const double2 *>(sA + (size_t)(1 % S) * C::A_STRIDE + ci);
+
+    for (int q = 2; q < nplanes; ++q) {
+        const int z = zs + q - 2;
+        const int stn = q % S, stc = (q - 1) % S;
+        mbar_wait(&full[stn], (uint32_t)((q / S) & 1));
+        const double2 anext = *reinterpret_cast<const double2 *>(sA + (size_t)stn * C::A_STRIDE + ci);
+        const double *pc = sA + (size_t)stc * C::A_STRIDE + ci;
+        const double xl = pc[-1], xr = pc[2];
+        const double2 ysv = *reinterpret_cast<const double2 *>(pc - C::BW);
+        const double2 ynv = *reinterpret_cast<const double2 *>(pc + C::BW);
+        const double2 ht = *reinterpret_cast<const double2 *>(sH + (size_t)stc * C::H_STRIDE + hi);
+
+        const double r0 = cell_residual(acur.x, xl, acur.y, ysv.x, ynv.x, aprev.x, anext.x, ht.x, p);
+        const double r1 = cell_residual(acur.y, acur.x, xr, ysv.y, ynv.y, aprev.y, anext.y, ht.y, p);
+        const double b0 = acur.x - p.dtau * r0;
+        const double b1 = acur.y - p.dtau * r1;
+        const size_t g = pxy + sz * z;
+
+        const bool plo = p.push_lo != nullptr && z == 1;
+        const bool phi = p.push_hi != nullptr && z == p.nz - 2;
+        double o0 = 0.0, o1 = 0.0;
+        if (plo || phi) {  // block-uniform
+            if (inb0) o0 = p.B[g];
+            if (inb1) o1 = p.B[g + 1];
+            if (p.consistent) {
+                if (valid0) o0 = b0;
+                if (valid1) o1 = b1;
+            }
+        }
+        if (valid0 && valid1) {
+            *reinterpret_cast<double2 *>(p.B + g) = make_double2(b0, b1);
+            if (p.R != nullptr) *reinterpret_cast<double2 *>(p.R + g) = make_double2(r0, r1);
+        } else {
+            if (valid0) { p.B[g] = b0; if (p.R != nullptr) p.R[g] = r0; }
+            if (valid1) { p.B[g + 1] = b1; if (p.R != nullptr) p.R[g + 1] = r1; }
+        }
+        if (valid0) { const double v = r0 * p.norm_scale; acc += v * v; }
+        if (valid1) { const double v = r1 * p.norm_scale; acc += v * v; }
+        if (plo) { if (inb0) p.push_lo[pxy] = o0; if (inb1) p.push_lo[pxy + 1] = o1; }
+        if (phi) { if (inb0) p.push_hi[pxy] = o0; if (inb1) p.push_hi[pxy + 1] = o1; }
+
+        __syncthreads();  // every thread is done with stage stc -> refill it
+        if (tid == 0 && q - 1 + S < nplanes) issue(q - 1 + S);
+        aprev = acur;
+        acur = anext;
+    }
+    if (p.push_lo != nullptr || p.push_hi != nullptr) __threadfence_system();
+    step_epilogue(p, acc, red);
+}
+
+// One block: consume the partial sums of all ranks in rank order (deterministic, identical on every GPU).
+// In-process handles pass `local` (nranks contiguous doubles on this device); one-process-per-GPU handles pass `slots`
+// and wait (bounded) for the peers' stores.
+__global__ void pt_finalize_kernel(PTState *state, double *err_hist, const double *local, RankSlots *slots, int nranks,
+                                   long long timeout_cycles)
+{
+    if (state->done) return;
+    __shared__ double vals[kMaxRanks];
+    __shared__ int failed;
+    const int t = threadIdx.x;
+    if (t == 0) failed = 0;
+    __syncthreads();
+    if (slots != nullptr) {
+        const unsigned long long seq = state->seq;
+        const int g = (int)(seq & 1ull);
+        if (t < nranks) {
+            const long long t0 = clock64();
+            bool ok = true;
+            while (ld_acquire_sys_u64(&slots->seq[g][t]) != seq) {
+                if (clock64() - t0 > timeout_cycles) { ok = false; break; }
+                __nanosleep(64);
+            }
+            if (!ok) failed = 1;
+            vals[t] = ld_relaxed_sys_f64(&slots->value[g][t]);
+        }
+    } else if (t < nranks) {
+        vals[t] = local[t];
+    }
+    __syncthreads();
+    if (t == 0) {
+        if (failed) {
+            state->error = 1;
+            state->done = 1;
+        } else {
+            double total = 0.0;
+            for (int r = 0; r < nranks; ++r) total += vals[r];  // MPI.Allreduce!(+) in rank order
+            state->seq += 1;
+            pt_finalize(state, total, err_hist);
+        }
+    }
+}
+
+}  // namespace b2s

@@ -1,0 +1,183 @@
+"""GPU parity of hot path 1 (3-D pseudo-transient diffusion) against the CPU oracle, through the C ABI.
+
+Bar: bit-exact fields on one GPU (library built with -fmad=false; the oracle with -ffp-contract=off), the residual
+norm within 1e-12 relative (summation order differs), identical iteration counts.
+Reference: scripts-part1/part1_kernel_programming.jl:46-58,99-228; test/part1.jl.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+REL_NORM_TOL = 1e-12  # tolerance on err (Float64, different summation order); fields are compared bit-exactly
+
+
+def _mk(b2s, *a, **k):
+    from b200stencil import part1
+    return part1.Diffusion3D(*a, **k)
+
+
+@pytest.mark.parametrize("variant", ["direct", "tma"])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 64, 32), (66, 34, 20), (96, 50, 40)])
+def test_l0_step_matches_oracle(b2s, gpu, oracle, variant, shape):
+    import torch
+    from b200stencil import capi
+    nx, ny, nz = shape
+    kv = capi.KERNEL_DIRECT if variant == "direct" else capi.KERNEL_TMA
+    rng = np.random.default_rng(7)
+    o = oracle.Diffusion3D(nx, ny, nz)
+    # random fields exercise every stencil arm; B pre-filled to check boundary cells stay untouched
+    Ht = np.asfortranarray(rng.standard_normal(shape))
+    A = np.asfortranarray(rng.standard_normal(shape))
+    B0 = np.asfortranarray(rng.standard_normal(shape))
+    dev = torch.device("cuda:0")
+    tHt = torch.from_numpy(Ht.ravel(order="F").copy()).to(dev)
+    tA = torch.from_numpy(A.ravel(order="F").copy()).to(dev)
+    tB = torch.from_numpy(B0.ravel(order="F").copy()).to(dev)
+    tR = torch.zeros_like(tA)
+    tS = torch.zeros(1, dtype=torch.float64, device=dev)
+    dx, dy, dz, dt, dtau = o.dx, o.dy, o.dz, o.dt, o.dtau
+    L = capi.lib()
+    capi.check(L.b2s_diffusion3d_step_tau(capi.ptr(tHt), capi.ptr(tA), capi.ptr(tB), capi.ptr(tR), nx, ny, nz, dtau,
+                                          1.0 / dt, 1.0 / dx, 1.0 / dy, 1.0 / dz, 1.0 / dx, 1.0 / dy, 1.0 / dz, dt,
+                                          capi.ptr(tS), kv, None))
+    torch.cuda.synchronize()
+    # numpy restatement with the oracle's operation order (elementwise numpy never contracts to FMA)
+    c = A[1:-1, 1:-1, 1:-1]
+    mD = (-1.0 / dx, -1.0 / dy, -1.0 / dz)
+    r = (((mD[0] * (A[2:, 1:-1, 1:-1] - c)) - (mD[0] * (c - A[:-2, 1:-1, 1:-1]))) * (1.0 / dx) +
+         ((mD[1] * (A[1:-1, 2:, 1:-1] - c)) - (mD[1] * (c - A[1:-1, :-2, 1:-1]))) * (1.0 / dy) +
+         ((mD[2] * (A[1:-1, 1:-1, 2:] - c)) - (mD[2] * (c - A[1:-1, 1:-1, :-2]))) * (1.0 / dz) +
+         (c - Ht[1:-1, 1:-1, 1:-1]) * (1.0 / dt))
+    Bref = B0.copy()
+    Bref[1:-1, 1:-1, 1:-1] = c - dtau * r
+    Rref = np.zeros(shape, order="F")
+    Rref[1:-1, 1:-1, 1:-1] = r
+    Bg = tB.cpu().numpy().reshape(shape, order="F")
+    Rg = tR.cpu().numpy().reshape(shape, order="F")
+    assert np.array_equal(Bg, Bref)
+    assert np.array_equal(Rg, Rref)
+    ss = float(np.sum((r * dt) ** 2))
+    assert abs(tS.item() - ss) <= REL_NORM_TOL * ss
+
+
+@pytest.mark.parametrize("variant", ["direct", "tma", "auto"])
+def test_iterate_fields_bit_exact(b2s, gpu, oracle, variant):
+    from b200stencil import capi
+    kv = {"direct": capi.KERNEL_DIRECT, "tma": capi.KERNEL_TMA, "auto": capi.KERNEL_AUTO}[variant]
+    n = (64, 64, 64)
+    o = oracle.Diffusion3D(*n)
+    g = _mk(b2s, *n, kernel_variant=kv)
+    g.init_gaussian()
+    assert np.array_equal(g.get("Ht"), o.get("Ht"))
+    for chunk in (1, 2, 37):
+        eo = o.iterate(chunk)
+        eg = g.iterate(chunk)
+        assert np.allclose(eg, eo, rtol=REL_NORM_TOL, atol=0.0)
+        assert np.array_equal(g.get("Htau"), o.get("Htau"))
+        assert np.array_equal(g.get("Htau2"), o.get("Htau2"))
+    g.close()
+
+
+def test_part1_default_run_counts_and_golden(b2s, gpu, oracle):
+    """scripts-part1/part1.jl defaults (config #1): 32^3, ttot=1, tol=1e-8 -> [188,187,185,184,183], test_1.bson."""
+    from b200stencil import part1
+    X, H, res, iters = part1.diffusion_3D_kernel_programming(nx=32, ny=32, nz=32, verbose=False, return_iters=True)
+    assert iters == [188, 187, 185, 184, 183]
+    o = oracle.Diffusion3D(32, 32, 32)
+    assert o.run(ttot=1.0, tol=1e-8) == iters
+    assert np.array_equal(H, o.gather())
+    gold = json.load(open(os.path.join(GOLDEN, "part1_test_1.json")))
+    inds = [int(np.ceil(v)) - 1 for v in np.linspace(1, 32, 12)]  # test/part1.jl:26
+    Hs = H[np.ix_(inds, inds, [14])][:, :, 0]
+    Href = np.array(gold["H"]["data_column_major"]).reshape(gold["H"]["size"], order="F")
+    assert np.allclose(Hs, Href, atol=1e-5, rtol=0)  # test/part1.jl:38-40
+    Xref = np.array(gold["X"]["data_column_major"])
+    assert np.allclose(X[inds], Xref, atol=1e-5, rtol=0)
+
+
+def test_published_point_values(b2s, gpu):
+    """benchmark-results/error_vs_grid_size_experiment_results.csv: H at (4.5,4.5,4.5), ttot=2, tol=1e-6, 17 digits."""
+    from b200stencil import part1
+    kats = json.load(open(os.path.join(GOLDEN, "part1_kats.json")))
+    for rec in kats["point_values_vs_grid_size"]:
+        n = rec["nx"]
+        if n > 64:
+            continue
+        X, H, _ = part1.diffusion_3D_kernel_programming(nx=n, ny=n, nz=n, ttot=2.0, tol=1e-6, verbose=False)
+        dx = 10.0 / n
+        ix = int(round(4.5 / dx + 1)) - 1
+        assert repr(float(H[ix, ix, ix])) == rec["val_str"], (n, H[ix, ix, ix], rec["val_str"])
+
+
+@pytest.mark.parametrize("halo_mode", [0, 1])
+@pytest.mark.parametrize("shape,nslabs,variant", [((64, 64, 34), 2, "tma"), ((32, 32, 18), 3, "direct"),
+                                                  ((64, 32, 18), 4, "tma")])
+def test_multislab_one_gpu_matches_rank_emulation(b2s, gpu, oracle, halo_mode, shape, nslabs, variant):
+    """z-slabs hosted on one GPU vs the oracle's emulated MPI ranks, dims=(1,1,N): lag-2 (reference) and consistent
+    halo semantics, literal BC quirk (D6). Current buffer and Ht must be bit-exact incl. halo planes."""
+    from b200stencil import capi
+    kv = capi.KERNEL_DIRECT if variant == "direct" else capi.KERNEL_TMA
+    o = oracle.Diffusion3D(*shape, dims=(1, 1, nslabs), halo_mode=halo_mode)
+    g = _mk(b2s, *shape, nslabs=nslabs, devices=[0] * nslabs, halo_mode=halo_mode, kernel_variant=kv)
+    g.init_gaussian()
+    for r in range(nslabs):
+        assert np.array_equal(g.get("Ht", r), o.get("Ht", r))
+    done = 0
+    for chunk in (1, 1, 1, 2, 5, 30):
+        eo = o.iterate(chunk)
+        eg = g.iterate(chunk)
+        done += chunk
+        assert np.allclose(eg, eo, rtol=REL_NORM_TOL, atol=0.0), done
+        for r in range(nslabs):
+            assert np.array_equal(g.get("Htau", r), o.get("Htau", r)), (done, r)
+    it_o, err_o = o.solve_timestep(1e-6)
+    it_g, err_g = g.solve_timestep(1e-6)
+    assert it_g == it_o
+    o.advance_time(); g.advance_time()
+    nz = shape[2]
+    Hg, Ho = g.gather(), o.gather()
+    assert np.array_equal(Hg, Ho)
+    g.close()
+
+
+def test_solve_timestep_iter_max_and_errors(b2s, gpu):
+    from b200stencil import capi, part1
+    g = _mk(b2s, 32, 32, 32)
+    g.init_gaussian()
+    it, err = g.solve_timestep(1e-30, iter_max=17)  # silently stops at iter_max (part1_kernel_programming.jl:179)
+    assert it == 17 and err > 1e-30
+    it, err = g.solve_timestep(1e-3, iter_max=0)
+    assert it == 0 and err == 2e-3
+    g.close()
+    with pytest.raises(capi.B2SError):
+        part1.Diffusion3D(2, 32, 32)
+    with pytest.raises(capi.B2SError):
+        part1.Diffusion3D(33, 32, 32, kernel_variant=capi.KERNEL_TMA)  # odd nx cannot use the TMA variant
+
+
+def test_512_properties(b2s, gpu):
+    """Full-size (512^3) checks that need no oracle run: both kernel variants agree bit-for-bit after 6 iterations,
+    the field keeps the x<->y<->z symmetry of the problem, the norm history decreases."""
+    from b200stencil import capi
+    n = (512, 512, 512)
+    outs = []
+    for kv in (capi.KERNEL_TMA, capi.KERNEL_DIRECT):
+        g = _mk(b2s, *n, kernel_variant=kv)
+        g.init_gaussian()
+        e = g.iterate(6)
+        outs.append((g.get("Htau"), e))
+        g.close()
+    (Ha, ea), (Hb, eb) = outs
+    assert np.array_equal(Ha, Hb)
+    assert np.allclose(ea, eb, rtol=REL_NORM_TOL, atol=0)
+    assert np.all(np.isfinite(ea)) and np.all(ea > 0)
+    sub = Ha[200:312:7, 200:312:7, 200:312:7]
+    assert np.array_equal(sub, sub.transpose(1, 0, 2))  # (x-term + y-term) commutes -> bitwise x<->y symmetry
+    assert np.allclose(sub, sub.transpose(2, 1, 0), rtol=1e-12, atol=0)
