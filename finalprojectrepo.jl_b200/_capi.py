@@ -74,6 +74,7 @@ SIGNATURES = {
     "b2s_diff3d_create": (_i, [C.POINTER(_vp), C.POINTER(Diff3DConfig)]),
     "b2s_diff3d_destroy": (_i, [_vp]),
     "b2s_diff3d_get_params": (_i, [_vp, C.POINTER(Diff3DParams)]),
+    "b2s_diff3d_params_for": (_i, [C.POINTER(Diff3DConfig), C.POINTER(Diff3DParams)]),
     "b2s_diff3d_init_gaussian": (_i, [_vp]),
     "b2s_diff3d_set_initial": (_i, [_vp, _vp]),
     "b2s_diff3d_ipc_blob_bytes": (_sz, []),

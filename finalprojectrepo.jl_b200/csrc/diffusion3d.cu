@@ -365,11 +365,9 @@ int ensure_hist(b2s_diff3d *h, int n)
     return B2S_OK;
 }
 
-void compute_params(b2s_diff3d *h)
+void compute_params_raw(const b2s_diff3d_config &c, b2s_diff3d_params &p)
 {
     // part1_kernel_programming.jl:104-131 with dims = (1,1,nslabs_total)
-    const b2s_diff3d_config &c = h->cfg;
-    b2s_diff3d_params &p = h->prm;
     const double D = 1.0;
     p.lx = 10.0; p.ly = 10.0; p.lz = 10.0;
     if (c.scale_physical_size) { p.lx = 1 * 10.0; p.ly = 1 * 10.0; p.lz = c.nslabs_total * 10.0; }
@@ -379,6 +377,13 @@ void compute_params(b2s_diff3d *h)
     p.dt = 0.2;
     const double m = fmin(p.dx, fmin(p.dy, p.dz));
     p.dtau = m * m / D / 8.1;
+}
+
+void compute_params(b2s_diff3d *h)
+{
+    compute_params_raw(h->cfg, h->prm);
+    const b2s_diff3d_params &p = h->prm;
+    const double D = 1.0;
     h->_dt = 1.0 / p.dt; h->_dx = 1.0 / p.dx; h->_dy = 1.0 / p.dy; h->_dz = 1.0 / p.dz;
     h->D_dx = D / p.dx; h->D_dy = D / p.dy; h->D_dz = D / p.dz;
 }
@@ -574,6 +579,14 @@ int b2s_diff3d_destroy(b2s_diff3d *h)
     cudaGetDevice(&prev);
     destroy_impl(h);
     if (prev >= 0) cudaSetDevice(prev);
+    return B2S_OK;
+}
+
+int b2s_diff3d_params_for(const b2s_diff3d_config *cfg, b2s_diff3d_params *out)
+{
+    B2S_REQUIRE(cfg && out, B2S_ERR_BAD_ARG, "NULL argument");
+    B2S_REQUIRE(cfg->nx >= 3 && cfg->ny >= 3 && cfg->nz >= 3 && cfg->nslabs_total >= 1, B2S_ERR_BAD_SIZE, "bad grid");
+    compute_params_raw(*cfg, *out);
     return B2S_OK;
 }
 

@@ -1,0 +1,613 @@
+// multigrid2d.cu -- host side of hot path 2: L0 wrappers (1:1 with the reference's call sites) and the L1 multigrid
+// handle (level table allocated once, fine levels as fused global-memory kernels, all coarse levels collapsed into one
+// shared-memory kernel, the whole V-cycle captured in a CUDA graph whose per-call arguments live in device memory).
+//
+// Reference entry points mirrored: MGsolve_2DPoisson! / Vcycle_2DPoisson! (scripts-part2/multigrid.jl:41-170),
+// cg! (scripts-part2/krylov.jl:55-91).
+#include "multigrid2d_kernels.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+using namespace b2s;
+
+namespace {
+
+inline int rows_for(int nx, int ny)
+{
+    // ~16 resident blocks of 128 threads per SM (148 SMs) so the loads in flight cover the HBM latency, >= 4 rows/thread
+    const int bx = (nx + kMGBX - 1) / kMGBX;
+    int want = std::max(1, (148 * 16) / bx);
+    int rows = std::max(4, (ny + want - 1) / want);
+    return std::min(rows, std::max(ny, 1));
+}
+
+inline dim3 sweep_grid(int nx, int ny, int rows) { return dim3((nx + kMGBX - 1) / kMGBX, (ny + rows - 1) / rows, 1); }
+
+inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+constexpr size_t kCoarseSmemLimit = 200 * 1024;
+
+}  // namespace
+
+struct b2s_mg {
+    b2s_mg_config cfg;
+    int nlev = 0;  // total levels; level nlev-1 is the coarsest
+    int nx[kMaxLevels], ny[kMaxLevels];
+    double *u[kMaxLevels] = {}, *rhs[kMaxLevels] = {}, *tmp[kMaxLevels] = {};  // u/rhs for l >= 1, tmp for all
+    int first_smem = 0;  // first level handled by the collapsed kernel
+    size_t coarse_smem = 0;
+    MGCall *call_dev = nullptr, *call_pin = nullptr;
+    double *sumsq_dev = nullptr;  // [0] last sweep, [1] f, [2],[3] rbgs colours
+    double *sumsq_pin = nullptr;
+    int *sweeps_dev = nullptr;
+    double *partials = nullptr;
+    unsigned int *ticket = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long kernel_launches = 0;
+    long long launches_per_cycle = 0;
+    double last_ms = 0.0;
+};
+
+namespace {
+
+// Enqueues one V-cycle (multigrid.jl:91-170) on `st`; counts kernel launches.
+int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
+{
+    const b2s_mg_config &c = h->cfg;
+    const MGCall *cp = h->call_dev;
+    long long n = 0;
+    const bool rb = c.smoother == B2S_SMOOTH_RBGS;
+    // apply_boundary_conditions!(u) before the cycle (no-op unless cp->bc_before)
+    {
+        const int t = h->nx[0] + h->ny[0];
+        mg_bc_kernel<<<(t + 255) / 256, 256, 0, st>>>(cp, nullptr, h->nx[0], h->ny[0], 0);
+        ++n;
+    }
+    auto smooth2 = [&](int l, bool norm_on_last) {
+        const int nx = h->nx[l], ny = h->ny[l];
+        const int rows = rows_for(nx, ny);
+        if (rb) {
+            for (int s = 0; s < 2; ++s)
+                for (int colour = 0; colour < 2; ++colour) {
+                    RbgsArgs a = {};
+                    a.cp = cp; a.level = l; a.u = h->u[l]; a.rhs = h->rhs[l]; a.nx = nx; a.ny = ny; a.rows = rows;
+                    a.colour = colour; a.want_norm = (norm_on_last && s == 1);
+                    a.partials = h->partials; a.ticket = h->ticket; a.sumsq_out = h->sumsq_dev + 2;
+                    dim3 g(((nx + 1) / 2 + kMGBX - 1) / kMGBX, (ny + rows - 1) / rows, 1);
+                    mg_rbgs_kernel<<<g, kMGBX, 0, st>>>(a);
+                    ++n;
+                }
+            if (norm_on_last) {  // sumsq[0] = red + black
+                mg_axpy_kernel<<<1, 32, 0, st>>>(0.0, nullptr, h->sumsq_dev, 0, 3);
+                ++n;
+            }
+        } else {
+            for (int s = 0; s < 2; ++s) {
+                SweepArgs a = {};
+                a.cp = cp; a.level = l; a.nx = nx; a.ny = ny; a.rows = rows; a.alpha = 4.0 / 5.0; a.mode = 1;
+                a.rhs = h->rhs[l];
+                a.u = s == 0 ? h->u[l] : h->tmp[l];
+                a.out = s == 0 ? h->tmp[l] : h->u[l];
+                a.swap_io = s;
+                a.want_norm = (norm_on_last && s == 1);
+                a.partials = h->partials; a.ticket = h->ticket; a.sumsq_out = h->sumsq_dev;
+                mg_sweep_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, st>>>(a);
+                ++n;
+            }
+        }
+    };
+    const int fs = h->first_smem;
+    // downward leg on the global-memory levels
+    for (int l = 0; l < fs; ++l) {
+        smooth2(l, false);
+        RestrictArgs r = {};
+        r.cp = cp; r.level = l; r.u = h->u[l]; r.rhs = h->rhs[l]; r.coarse = h->rhs[l + 1]; r.zero_out = h->u[l + 1];
+        r.nx = h->nx[l]; r.ny = h->ny[l]; r.nxc = h->nx[l + 1]; r.nyc = h->ny[l + 1];
+        r.from_res = 1; r.full_weighting = c.restriction == B2S_RESTRICT_FW;
+        dim3 g((r.nxc + 63) / 64, (r.nyc + 3) / 4, 1);
+        mg_restrict_kernel<<<g, dim3(64, 4, 1), 0, st>>>(r);
+        ++n;
+    }
+    // collapsed coarse hierarchy
+    {
+        CoarseArgs a = {};
+        a.cp = cp; a.level0 = fs; a.nlev = h->nlev - fs;
+        for (int l = fs; l < h->nlev; ++l) { a.nx[l - fs] = h->nx[l]; a.ny[l - fs] = h->ny[l]; }
+        a.rhs_in = fs == 0 ? nullptr : h->rhs[fs];
+        a.u_io = fs == 0 ? nullptr : h->u[fs];
+        a.u_is_input = fs == 0 ? 1 : 0;
+        a.coarse_solve_size = c.coarse_solve_size; a.coarse_solver = c.coarse_solver;
+        a.smoother = c.smoother; a.restriction = c.restriction;
+        a.sumsq_out = fs == 0 ? h->sumsq_dev : nullptr;
+        mg_coarse_kernel<<<1, 1024, h->coarse_smem, st>>>(a);
+        ++n;
+    }
+    // upward leg
+    for (int l = fs - 1; l >= 0; --l) {
+        const int nx = h->nx[l], ny = h->ny[l];
+        const int rows = rows_for(nx, ny);
+        if (rb) {
+            ProlongArgs p = {};
+            p.cp = cp; p.level = l; p.coarse = h->u[l + 1]; p.fine = h->u[l]; p.nx = nx; p.ny = ny;
+            p.nxc = h->nx[l + 1]; p.nyc = h->ny[l + 1]; p.rows = rows; p.mode = 1;
+            mg_prolong_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, st>>>(p);
+            ++n;
+            smooth2(l, l == 0);
+        } else {
+            // fused prolongation + correction + first post-smoothing sweep, then the second sweep
+            ProlongSmoothArgs p = {};
+            p.cp = cp; p.level = l; p.coarse = h->u[l + 1]; p.u = h->u[l]; p.rhs = h->rhs[l]; p.out = h->tmp[l];
+            p.nx = nx; p.ny = ny; p.nxc = h->nx[l + 1]; p.nyc = h->ny[l + 1]; p.rows = rows;
+            mg_prolong_smooth_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, st>>>(p);
+            ++n;
+            SweepArgs a = {};
+            a.cp = cp; a.level = l; a.nx = nx; a.ny = ny; a.rows = rows; a.alpha = 4.0 / 5.0; a.mode = 1;
+            a.rhs = h->rhs[l]; a.u = h->tmp[l]; a.out = h->u[l]; a.swap_io = 1;
+            a.want_norm = (l == 0);
+            a.partials = h->partials; a.ticket = h->ticket; a.sumsq_out = h->sumsq_dev;
+            mg_sweep_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, st>>>(a);
+            ++n;
+        }
+    }
+    B2S_CUDA(cudaGetLastError());
+    if (count) *count = n;
+    return B2S_OK;
+}
+
+int launch_cycle(b2s_mg *h)
+{
+    if (h->cfg.use_graph) {
+        if (!h->graph) {
+            cudaGraph_t g = nullptr;
+            B2S_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            long long n = 0;
+            int rc = enqueue_vcycle(h, h->stream, &n);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            if (rc != B2S_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            B2S_CUDA(e);
+            h->launches_per_cycle = n;
+            B2S_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+            B2S_CUDA(cudaGraphDestroy(g));
+        }
+        B2S_CUDA(cudaGraphLaunch(h->graph, h->stream));
+        h->kernel_launches += h->launches_per_cycle;
+    } else {
+        long long n = 0;
+        B2S_CHECK(enqueue_vcycle(h, h->stream, &n));
+        h->kernel_launches += n;
+    }
+    return B2S_OK;
+}
+
+int set_call(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int apply_bcs, int bc_before)
+{
+    MGCall &m = *h->call_pin;
+    m.u = u; m.rhs = f; m.h = hgrid; m.c = c; m.tol = tol; m.apply_bcs = apply_bcs; m.bc_before = bc_before;
+    m.sumsq = h->sumsq_dev; m.coarse_sweeps = h->sweeps_dev;
+    B2S_CUDA(cudaMemcpyAsync(h->call_dev, h->call_pin, sizeof(MGCall), cudaMemcpyHostToDevice, h->stream));
+    return B2S_OK;
+}
+
+int mg_destroy_impl(b2s_mg *h)
+{
+    if (!h) return B2S_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (h->u[l]) cudaFree(h->u[l]);
+        if (h->rhs[l]) cudaFree(h->rhs[l]);
+        if (h->tmp[l]) cudaFree(h->tmp[l]);
+    }
+    if (h->call_dev) cudaFree(h->call_dev);
+    if (h->call_pin) cudaFreeHost(h->call_pin);
+    if (h->sumsq_dev) cudaFree(h->sumsq_dev);
+    if (h->sumsq_pin) cudaFreeHost(h->sumsq_pin);
+    if (h->sweeps_dev) cudaFree(h->sweeps_dev);
+    if (h->partials) cudaFree(h->partials);
+    if (h->ticket) cudaFree(h->ticket);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2S_OK;
+}
+
+// sum f^2 over all entries into sumsq_dev[1]
+int enqueue_fnorm(b2s_mg *h)
+{
+    mg_reduce_kernel<<<kReduceBlocks, kReduceThreads, 0, h->stream>>>(nullptr, nullptr, (size_t)h->nx[0] * h->ny[0], h->partials,
+                                                                      h->ticket, h->sumsq_dev + 1, h->call_dev, 1);
+    B2S_CUDA(cudaGetLastError());
+    h->kernel_launches += 1;
+    return B2S_OK;
+}
+
+}  // namespace
+
+// internal (ns2d.cu): the stream all work of a handle is ordered on
+cudaStream_t b2s_mg_stream_internal(b2s_mg *h) { return h->stream; }
+void b2s_mg_count_launches_internal(b2s_mg *h, long long n) { h->kernel_launches += n; }
+
+extern "C" {
+
+int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
+{
+    B2S_REQUIRE(out && cfg, B2S_ERR_BAD_ARG, "NULL argument");
+    *out = nullptr;
+    const int nx = cfg->nx, ny = cfg->ny, cs = cfg->coarse_solve_size;
+    B2S_REQUIRE(nx >= 3 && ny >= 3, B2S_ERR_BAD_SIZE, "grid %dx%d too small", nx, ny);
+    // asserts multigrid.jl:45-46
+    B2S_REQUIRE(cs <= std::min(nx, ny), B2S_ERR_BAD_SIZE, "coarse_solve_size %d > min(nx, ny) = %d", cs, std::min(nx, ny));
+    B2S_REQUIRE(cs >= 2 && pow2(cs - 1), B2S_ERR_BAD_SIZE, "coarse_solve_size - 1 = %d is not a power of 2", cs - 1);
+    B2S_REQUIRE(cfg->coarse_solver == B2S_COARSE_JACOBI || cfg->coarse_solver == B2S_COARSE_CG, B2S_ERR_BAD_ARG, "bad coarse_solver");
+    B2S_REQUIRE(cfg->smoother == B2S_SMOOTH_JACOBI || cfg->smoother == B2S_SMOOTH_RBGS, B2S_ERR_BAD_ARG, "bad smoother");
+    B2S_REQUIRE(cfg->restriction == B2S_RESTRICT_INJECT || cfg->restriction == B2S_RESTRICT_FW, B2S_ERR_BAD_ARG, "bad restriction");
+    int ndev = 0;
+    B2S_CHECK(b2s_device_count(&ndev));
+    B2S_REQUIRE(ndev > 0, B2S_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    B2S_REQUIRE(cfg->device >= 0 && cfg->device < ndev, B2S_ERR_BAD_ARG, "device %d out of range", cfg->device);
+
+    b2s_mg *h = new b2s_mg();
+    h->cfg = *cfg;
+    // level table: halve until min(nx, ny) <= coarse_solve_size; every halving needs even nx-1, ny-1 (multigrid.jl:95-97)
+    int lx = nx, ly = ny, L = 0;
+    for (;;) {
+        if (L >= kMaxLevels) { delete h; set_error("too many levels"); return B2S_ERR_BAD_SIZE; }
+        h->nx[L] = lx; h->ny[L] = ly; ++L;
+        if (((lx - 1) & 1) || ((ly - 1) & 1)) {
+            delete h;
+            set_error("ERROR:not a power of 2 (level %d is %dx%d)", L - 1, lx, ly);
+            return B2S_ERR_BAD_SIZE;
+        }
+        if (std::min(lx, ly) <= cs) break;
+        lx = 1 + (lx - 1) / 2; ly = 1 + (ly - 1) / 2;
+    }
+    h->nlev = L;
+    // which levels fit into the collapsed shared-memory kernel (3 arrays per level + CG scratch of the coarsest)
+    {
+        size_t bytes = 4 * (size_t)h->nx[L - 1] * h->ny[L - 1] * 8 + 64;
+        int fs = L;
+        for (int l = L - 1; l >= 0; --l) {
+            const size_t add = 3 * (size_t)h->nx[l] * h->ny[l] * 8;
+            if (bytes + add > kCoarseSmemLimit) break;
+            if (!cfg->smem_levels && l < L - 1) break;
+            bytes += add;
+            fs = l;
+        }
+        if (fs == L) {
+            set_error("coarsest level %dx%d does not fit into shared memory (not implemented)", h->nx[L - 1], h->ny[L - 1]);
+            delete h;
+            return B2S_ERR_NOT_IMPLEMENTED;
+        }
+        h->first_smem = fs;
+        h->coarse_smem = bytes;
+    }
+    DeviceGuard guard;
+    guard.set(cfg->device);
+#define MG_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+            mg_destroy_impl(h);                                                                \
+            return B2S_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+    MG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MG_CUDA(cudaEventCreate(&h->ev0));
+    MG_CUDA(cudaEventCreate(&h->ev1));
+    for (int l = 0; l < L; ++l) {
+        const size_t bytes = (size_t)h->nx[l] * h->ny[l] * 8;
+        if (l < std::max(h->first_smem, 1)) {
+            MG_CUDA(cudaMalloc(&h->tmp[l], bytes));
+            MG_CUDA(cudaMemset(h->tmp[l], 0, bytes));
+        }
+        if (l >= 1 && l <= h->first_smem) {
+            MG_CUDA(cudaMalloc(&h->u[l], bytes));
+            MG_CUDA(cudaMalloc(&h->rhs[l], bytes));
+            MG_CUDA(cudaMemset(h->u[l], 0, bytes));
+            MG_CUDA(cudaMemset(h->rhs[l], 0, bytes));
+        }
+    }
+    MG_CUDA(cudaMalloc(&h->call_dev, sizeof(MGCall)));
+    MG_CUDA(cudaMallocHost(&h->call_pin, sizeof(MGCall)));
+    MG_CUDA(cudaMalloc(&h->sumsq_dev, 8 * sizeof(double)));
+    MG_CUDA(cudaMemset(h->sumsq_dev, 0, 8 * sizeof(double)));
+    MG_CUDA(cudaMallocHost(&h->sumsq_pin, 8 * sizeof(double)));
+    MG_CUDA(cudaMalloc(&h->sweeps_dev, 4 * sizeof(int)));
+    MG_CUDA(cudaMemset(h->sweeps_dev, 0, 4 * sizeof(int)));
+    MG_CUDA(cudaMalloc(&h->partials, sizeof(double) * kMaxPartials));
+    MG_CUDA(cudaMalloc(&h->ticket, 64));
+    MG_CUDA(cudaMemset(h->ticket, 0, 64));
+    MG_CUDA(cudaFuncSetAttribute(mg_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemLimit + 1024));
+#undef MG_CUDA
+    *out = h;
+    return B2S_OK;
+}
+
+int b2s_mg_destroy(b2s_mg *h)
+{
+    int prev = -1;
+    cudaGetDevice(&prev);
+    mg_destroy_impl(h);
+    if (prev >= 0) cudaSetDevice(prev);
+    return B2S_OK;
+}
+
+int b2s_mg_solve(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int niters, int apply_bcs,
+                 double *r_rms_out, int *ncycles, double *rel_hist)
+{
+    B2S_REQUIRE(h && u && f, B2S_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard;
+    guard.set(h->cfg.device);
+    const double N = (double)h->nx[0] * h->ny[0];
+    B2S_CUDA(cudaEventRecord(h->ev0, h->stream));
+    B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs));
+    B2S_CHECK(enqueue_fnorm(h));  // f_rms = sqrt(sum(f.^2)/(nx*ny))   multigrid.jl:53
+    double r_rms = 0.0, f_rms = 0.0, tolf = 0.0;
+    int n = 0;
+    for (int iter = 1; iter <= niters; ++iter) {
+        B2S_CHECK(launch_cycle(h));
+        B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        B2S_CUDA(cudaStreamSynchronize(h->stream));  // @synchronize()   multigrid.jl:65
+        if (iter == 1) {
+            f_rms = sqrt(h->sumsq_pin[1] / N);
+            tolf = tol * f_rms;
+        }
+        r_rms = sqrt(h->sumsq_pin[0] / N);
+        n = iter;
+        if (rel_hist) rel_hist[iter - 1] = r_rms / f_rms;
+        if (r_rms < tolf) break;  // multigrid.jl:70-75
+        if (r_rms != r_rms) break;
+    }
+    B2S_CUDA(cudaEventRecord(h->ev1, h->stream));
+    B2S_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    B2S_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    if (r_rms_out) *r_rms_out = r_rms;
+    if (ncycles) *ncycles = n;
+    return B2S_OK;
+}
+
+int b2s_mg_vcycle(b2s_mg *h, double *u, const double *rhs, double hgrid, double c, double tol, int apply_bcs, double *res_rms)
+{
+    B2S_REQUIRE(h && u && rhs, B2S_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard;
+    guard.set(h->cfg.device);
+    B2S_CHECK(set_call(h, u, rhs, hgrid, c, tol, apply_bcs, 0));
+    B2S_CHECK(launch_cycle(h));
+    B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    if (res_rms) *res_rms = sqrt(h->sumsq_pin[0] / ((double)h->nx[0] * h->ny[0]));
+    return B2S_OK;
+}
+
+int b2s_mg_cycles(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int ncycles, int apply_bcs,
+                  double *r_rms_last, double *ms_out)
+{
+    B2S_REQUIRE(h && u && f && ncycles >= 0, B2S_ERR_BAD_ARG, "bad argument");
+    DeviceGuard guard;
+    guard.set(h->cfg.device);
+    B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs));
+    if (h->cfg.use_graph && !h->graph && ncycles > 0) {  // keep graph instantiation out of the timed region
+        B2S_CHECK(launch_cycle(h));
+        B2S_CUDA(cudaStreamSynchronize(h->stream));
+        --ncycles;
+    }
+    B2S_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < ncycles; ++i) B2S_CHECK(launch_cycle(h));
+    B2S_CUDA(cudaEventRecord(h->ev1, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    B2S_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    if (ms_out) *ms_out = ms;
+    if (r_rms_last) *r_rms_last = sqrt(h->sumsq_pin[0] / ((double)h->nx[0] * h->ny[0]));
+    return B2S_OK;
+}
+
+int b2s_mg_last_coarse_sweeps(const b2s_mg *h, int *sweeps)
+{
+    B2S_REQUIRE(h && sweeps, B2S_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard;
+    guard.set(h->cfg.device);
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    B2S_CUDA(cudaMemcpy(sweeps, h->sweeps_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    return B2S_OK;
+}
+
+int b2s_mg_stats(const b2s_mg *h, long long *kernel_launches, double *last_call_ms)
+{
+    B2S_REQUIRE(h, B2S_ERR_BAD_ARG, "NULL handle");
+    if (kernel_launches) *kernel_launches = h->kernel_launches;
+    if (last_call_ms) *last_call_ms = h->last_ms;
+    return B2S_OK;
+}
+
+// ==================================================================================================================
+// L0 wrappers
+// ==================================================================================================================
+static int check_policy(int policy)
+{
+    // execution_policy == serial -> error()   multigrid.jl:233-236, krylov.jl:46-49 (serial is a CPU-only debug path)
+    B2S_REQUIRE(policy == B2S_POLICY_PARALLEL || policy == B2S_POLICY_PARALLEL_SHMEM, B2S_ERR_NOT_IMPLEMENTED,
+                "execution policy %d is not available on the GPU", policy);
+    return B2S_OK;
+}
+
+int b2s_residual2d(const double *u, const double *f, double h, double c, double *res, int nx, int ny, int policy, void *stream)
+{
+    B2S_REQUIRE(u && f && res && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_CHECK(check_policy(policy));
+    SweepArgs a = {};
+    a.u = u; a.rhs = f; a.out = res; a.nx = nx; a.ny = ny; a.rows = rows_for(nx, ny); a.h = h; a.c = c; a.alpha = 1.0;
+    a.mode = 0;
+    mg_sweep_kernel<<<sweep_grid(nx, ny, a.rows), kMGBX, 0, (cudaStream_t)stream>>>(a);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_iteration2d(double *u, const double *f, double h, double c, double *res, int nx, int ny, double alpha, int policy,
+                    double *r_rms_host, void *stream)
+{
+    B2S_REQUIRE(u && f && res && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_CHECK(check_policy(policy));
+    Scratch *sc = nullptr;
+    B2S_CHECK(get_scratch(&sc));
+    cudaStream_t st = (cudaStream_t)stream;
+    SweepArgs a = {};
+    a.u = u; a.rhs = f; a.out = res; a.nx = nx; a.ny = ny; a.rows = rows_for(nx, ny); a.h = h; a.c = c; a.alpha = alpha;
+    a.mode = 0; a.want_norm = 1; a.partials = sc->partials; a.ticket = sc->ticket; a.sumsq_out = sc->result;
+    mg_sweep_kernel<<<sweep_grid(nx, ny, a.rows), kMGBX, 0, st>>>(a);
+    B2S_CUDA(cudaGetLastError());
+    const double w = alpha * ((h * h) / (4.0 + c * (h * h)));
+    mg_axpy_kernel<<<296, 256, 0, st>>>(w, res, u, (size_t)nx * ny, 0);  // u .+= w .* res (res frame untouched by the kernel)
+    B2S_CUDA(cudaGetLastError());
+    B2S_CUDA(cudaMemcpyAsync(sc->pinned, sc->result, sizeof(double), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (r_rms_host) *r_rms_host = sqrt(sc->pinned[0] / ((double)nx * ny));
+    return B2S_OK;
+}
+
+int b2s_rbgs2d(double *u, const double *f, double h, double c, int nx, int ny, double *r_rms_host, void *stream)
+{
+    B2S_REQUIRE(u && f && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    Scratch *sc = nullptr;
+    B2S_CHECK(get_scratch(&sc));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = rows_for(nx, ny);
+    for (int colour = 0; colour < 2; ++colour) {
+        RbgsArgs a = {};
+        a.u = u; a.rhs = f; a.nx = nx; a.ny = ny; a.rows = rows; a.colour = colour; a.h = h; a.c = c; a.want_norm = 1;
+        a.partials = sc->partials; a.ticket = sc->ticket; a.sumsq_out = sc->result + 2;
+        dim3 g(((nx + 1) / 2 + kMGBX - 1) / kMGBX, (ny + rows - 1) / rows, 1);
+        mg_rbgs_kernel<<<g, kMGBX, 0, st>>>(a);
+        B2S_CUDA(cudaGetLastError());
+    }
+    B2S_CUDA(cudaMemcpyAsync(sc->pinned, sc->result + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (r_rms_host) *r_rms_host = sqrt((sc->pinned[0] + sc->pinned[1]) / ((double)nx * ny));
+    return B2S_OK;
+}
+
+static int restrict_common(const double *fine, double *coarse, int nx, int ny, int apply_bcs, int fw, void *stream)
+{
+    B2S_REQUIRE(fine && coarse && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_REQUIRE(((nx - 1) & 1) == 0 && ((ny - 1) & 1) == 0, B2S_ERR_BAD_SIZE, "ERROR:not a power of 2 (%dx%d)", nx, ny);
+    RestrictArgs r = {};
+    r.u = fine; r.coarse = coarse; r.nx = nx; r.ny = ny; r.nxc = 1 + (nx - 1) / 2; r.nyc = 1 + (ny - 1) / 2;
+    r.h = 1.0; r.from_res = 0; r.full_weighting = fw; r.apply_bcs = apply_bcs;
+    dim3 g((r.nxc + 63) / 64, (r.nyc + 3) / 4, 1);
+    mg_restrict_kernel<<<g, dim3(64, 4, 1), 0, (cudaStream_t)stream>>>(r);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+int b2s_restrict_inject2d(const double *fine, double *coarse, int nx, int ny, int apply_bcs, void *stream)
+{
+    return restrict_common(fine, coarse, nx, ny, apply_bcs, 0, stream);
+}
+int b2s_restrict_fw2d(const double *fine, double *coarse, int nx, int ny, int apply_bcs, void *stream)
+{
+    return restrict_common(fine, coarse, nx, ny, apply_bcs, 1, stream);
+}
+
+int b2s_prolongate2d(const double *coarse, double *fine, int nx, int ny, int apply_bcs, void *stream)
+{
+    B2S_REQUIRE(fine && coarse && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_REQUIRE(((nx - 1) & 1) == 0 && ((ny - 1) & 1) == 0, B2S_ERR_BAD_SIZE, "ERROR:not a power of 2 (%dx%d)", nx, ny);
+    ProlongArgs p = {};
+    p.coarse = coarse; p.fine = fine; p.nx = nx; p.ny = ny; p.nxc = 1 + (nx - 1) / 2; p.nyc = 1 + (ny - 1) / 2;
+    p.rows = rows_for(nx, ny); p.mode = 0; p.apply_bcs = apply_bcs;
+    mg_prolong_kernel<<<sweep_grid(nx, ny, p.rows), kMGBX, 0, (cudaStream_t)stream>>>(p);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_matvec2d(const double *T, double hx, double hy, double c, double *out, int nx, int ny, int policy, void *stream)
+{
+    B2S_REQUIRE(T && out && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_CHECK(check_policy(policy));
+    const int rows = rows_for(nx, ny);
+    mg_matvec_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, (cudaStream_t)stream>>>(T, hx, hy, c, out, nx, ny, rows);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_apply_bc2d(double *T, int nx, int ny, int kind, void *stream)
+{
+    B2S_REQUIRE(T && nx >= 3 && ny >= 3 && kind >= 0 && kind <= 2, B2S_ERR_BAD_ARG, "bad argument");
+    const int t = nx + ny;
+    mg_bc_kernel<<<(t + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nullptr, T, nx, ny, kind);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+static int reduce_common(const double *x, const double *y, size_t n, double *out_host, void *stream)
+{
+    B2S_REQUIRE(x && y && out_host, B2S_ERR_BAD_ARG, "NULL argument");
+    Scratch *sc = nullptr;
+    B2S_CHECK(get_scratch(&sc));
+    cudaStream_t st = (cudaStream_t)stream;
+    mg_reduce_kernel<<<kReduceBlocks, kReduceThreads, 0, st>>>(x, y, n, sc->partials, sc->ticket, sc->result, nullptr, 0);
+    B2S_CUDA(cudaGetLastError());
+    B2S_CUDA(cudaMemcpyAsync(sc->pinned, sc->result, sizeof(double), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    *out_host = sc->pinned[0];
+    return B2S_OK;
+}
+int b2s_dot(const double *x, const double *y, size_t n, double *out_host, void *stream) { return reduce_common(x, y, n, out_host, stream); }
+int b2s_sumsq(const double *x, size_t n, double *out_host, void *stream) { return reduce_common(x, x, n, out_host, stream); }
+
+int b2s_axpy(double alpha, const double *x, double *y, size_t n, void *stream)
+{
+    B2S_REQUIRE(x && y, B2S_ERR_BAD_ARG, "NULL argument");
+    mg_axpy_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(alpha, x, y, n, 0);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+int b2s_xpby(const double *x, double beta, double *y, size_t n, void *stream)
+{
+    B2S_REQUIRE(x && y, B2S_ERR_BAD_ARG, "NULL argument");
+    mg_axpy_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(beta, x, y, n, 1);
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_cg_solve(double *x, const double *b, double hx, double hy, double c, double tol, int nmax, int nx, int ny, int policy,
+                 double *res_rms, int *iters, void *stream)
+{
+    B2S_REQUIRE(x && b && nx >= 3 && ny >= 3, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_CHECK(check_policy(policy));
+    const size_t n = (size_t)nx * ny;
+    const size_t smem = 6 * n * sizeof(double);
+    B2S_REQUIRE(smem <= 220 * 1024, B2S_ERR_NOT_IMPLEMENTED,
+                "stand-alone cg! is implemented for grids of up to %d points (got %dx%d)", (int)(220 * 1024 / 48), nx, ny);
+    Scratch *sc = nullptr;
+    B2S_CHECK(get_scratch(&sc));
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr = false;
+    if (!attr) {
+        B2S_CUDA(cudaFuncSetAttribute(mg_cg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    int *it_dev = (int *)(sc->ticket + 2);
+    mg_cg_smem_kernel<<<1, 1024, smem, st>>>(x, b, hx, hy, c, tol, nmax, nx, ny, sc->result, it_dev);
+    B2S_CUDA(cudaGetLastError());
+    B2S_CUDA(cudaMemcpyAsync(sc->pinned, sc->result, sizeof(double), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaMemcpyAsync(sc->pinned + 1, it_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (res_rms) *res_rms = sqrt(sc->pinned[0] / ((double)nx * ny));
+    if (iters) *iters = *(int *)(sc->pinned + 1);
+    return B2S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,698 @@
+// multigrid2d_kernels.cuh -- device code of hot path 2: matrix-free geometric multigrid for (lap - c) u = f on a
+// 2-D node grid, its smoothers, transfer operators, the collapsed shared-memory coarse hierarchy and CG.
+//
+// Reference semantics (file:line relative to the reference repository):
+//   scripts-part2/multigrid.jl:173-188   residual_2DPoisson!       res = ((uE+uW+uN+uS - C u)*_h2 - f), interior
+//   scripts-part2/multigrid.jl:245-258   iteration_2DPoisson!      r_rms (pre-update) ; u += alpha*(h^2/C)*res
+//   scripts-part2/multigrid.jl:330-358   restrict! / wrapper       zero, injection at even (0-based) points, Neumann
+//   scripts-part2/multigrid.jl:403-472   prolongate* / wrapper     zero, bilinear scatter, Neumann  (here: a gather
+//                                                                  that reproduces the CPU arrival order, no atomics)
+//   scripts-part2/multigrid.jl:91-170    Vcycle_2DPoisson!
+//   scripts-part2/krylov.jl:7-13,55-91   matvec, cg!
+//   scripts-part2/part2_utils.jl:21-39   boundary conditions
+// All arithmetic in the order written there; the translation unit is compiled with -fmad=false.
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int kMaxLevels = 24;
+
+// Per-call arguments live in device memory so that a captured CUDA graph of the V-cycle is independent of them.
+struct MGCall {
+    double *u;          // finest-level unknown (caller's array)
+    const double *rhs;  // finest-level right-hand side (caller's array)
+    double h, c, tol;
+    int apply_bcs;      // Neumann handling inside restrict/prolongate (multigrid.jl:355-357,468-470)
+    int bc_before;      // apply_boundary_conditions!(u) before the cycle (multigrid.jl:60-62)
+    double *sumsq;      // [0]: sum res^2 of the last sweep on the finest level; [1]: sum f^2
+    int *coarse_sweeps; // sweeps / iterations of the coarsest solve
+};
+
+__device__ __forceinline__ double level_h(const MGCall *cp, int level)
+{
+    double h = cp->h;
+    for (int l = 0; l < level; ++l) h = h * 2;  // Vcycle(..., h*2, ...) multigrid.jl:133
+    return h;
+}
+
+struct Coef {
+    double C, _h2, w;
+};
+__device__ __forceinline__ Coef make_coef(double h, double c, double alpha)
+{
+    Coef k;
+    k.C = 4.0 + c * (h * h);
+    k._h2 = 1 / (h * h);
+    k.w = alpha * ((h * h) / (4.0 + c * (h * h)));
+    return k;
+}
+
+__device__ __forceinline__ double point_residual(const double *__restrict__ u, const double *__restrict__ f, int nx, size_t p,
+                                                 const Coef &k)
+{
+    return ((u[p + 1] + u[p - 1] + u[p + nx] + u[p - nx] - k.C * u[p]) * k._h2 - f[p]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fine-level (global memory) kernels. Thread block = 128 threads along x; each thread marches `rows` rows in y.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMGBX = 128;
+
+struct SweepArgs {
+    const MGCall *cp;
+    int level;          // 0: arrays come from *cp
+    const double *u;    // used when level > 0 or cp == nullptr
+    const double *rhs;
+    double *out;        // Jacobi: u_new ; residual: res
+    int nx, ny, rows;
+    double h, c, alpha; // used when cp == nullptr (L0 calls)
+    int mode;           // 0: residual only (interior of out) ; 1: Jacobi sweep out = u + w*res (frame copied)
+    int want_norm;
+    double *partials;
+    unsigned int *ticket;
+    double *sumsq_out;
+    int swap_io;        // level 0 ping-pong: 1 -> read tmp (u arg), write cp->u
+};
+
+__global__ void __launch_bounds__(kMGBX) mg_sweep_kernel(const SweepArgs a)
+{
+    __shared__ double red[32];
+    const double *u = a.u;
+    const double *rhs = a.rhs;
+    double *out = a.out;
+    double h = a.h, c = a.c;
+    if (a.cp != nullptr) {
+        c = a.cp->c;
+        h = level_h(a.cp, a.level);
+        if (a.level == 0) {
+            rhs = a.cp->rhs;
+            if (a.swap_io) out = a.cp->u; else u = a.cp->u;
+        }
+    }
+    const Coef k = make_coef(h, c, a.alpha);
+    const int nx = a.nx, ny = a.ny;
+    const int i = blockIdx.x * kMGBX + threadIdx.x;
+    const int j0 = blockIdx.y * a.rows;
+    const int j1 = min(j0 + a.rows, ny);
+    double acc = 0.0;
+    if (i < nx) {
+        const bool xin = i >= 1 && i <= nx - 2;
+        for (int j = j0; j < j1; ++j) {
+            const size_t p = (size_t)i + (size_t)nx * j;
+            const bool interior = xin && j >= 1 && j <= ny - 2;
+            if (interior) {
+                const double r = point_residual(u, rhs, nx, p, k);
+                if (a.want_norm) acc += r * r;
+                out[p] = a.mode == 0 ? r : u[p] + k.w * r;
+            } else if (a.mode == 1) {
+                out[p] = u[p];  // u += w*res with res == 0 on the frame
+            }
+        }
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+    }
+}
+
+// Red-black Gauss-Seidel half sweep in place (variant B). colour 0 = (i+j) even. Accumulates pre-update res^2 into
+// sumsq_out[colour] when want_norm.
+struct RbgsArgs {
+    const MGCall *cp;
+    int level;
+    double *u;
+    const double *rhs;
+    int nx, ny, rows, colour;
+    double h, c;
+    int want_norm;
+    double *partials;
+    unsigned int *ticket;
+    double *sumsq_out;
+};
+
+__global__ void __launch_bounds__(kMGBX) mg_rbgs_kernel(const RbgsArgs a)
+{
+    __shared__ double red[32];
+    double *u = a.u;
+    const double *rhs = a.rhs;
+    double h = a.h, c = a.c;
+    if (a.cp != nullptr) {
+        c = a.cp->c;
+        h = level_h(a.cp, a.level);
+        if (a.level == 0) { u = a.cp->u; rhs = a.cp->rhs; }
+    }
+    const double C = 4.0 + c * (h * h), h2 = h * h, w = 1.0 * (h2 / C);
+    const int nx = a.nx, ny = a.ny;
+    // each thread owns every second point of a row
+    const int t = blockIdx.x * kMGBX + threadIdx.x;
+    const int j0 = max(1, blockIdx.y * a.rows), j1 = min(blockIdx.y * a.rows + a.rows, ny - 1);
+    double acc = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const int i = 1 + ((1 + j + a.colour) & 1) + 2 * t;
+        if (i <= nx - 2) {
+            const size_t p = (size_t)i + (size_t)nx * j;
+            const double r = (u[p + 1] + u[p - 1] + u[p + nx] + u[p - nx] - C * u[p]) / h2 - rhs[p];
+            u[p] = u[p] + w * r;
+            acc += r * r;
+        }
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) a.sumsq_out[a.colour] = total;
+    }
+}
+
+// Coarse right-hand side from the fine level: zero frame, injection or full weighting of the fine residual (FROM_RES:
+// computed on the fly from u and rhs -- fused residual + restriction) or of a given fine field, Neumann copy.
+struct RestrictArgs {
+    const MGCall *cp;
+    int level;             // fine level
+    const double *u;       // fine unknown (FROM_RES) or the fine field to restrict
+    const double *rhs;     // fine rhs (FROM_RES)
+    double *coarse;
+    double *zero_out;      // nullable: coarse-level unknown, reset to 0 in the same pass (corr_c .= 0, multigrid.jl:132)
+    int nx, ny, nxc, nyc;
+    double h, c;
+    int from_res, full_weighting, apply_bcs;
+};
+
+template <bool FROM_RES>
+__device__ __forceinline__ double fine_value(const double *__restrict__ u, const double *__restrict__ f, int nx, int i, int j,
+                                             const Coef &k)
+{
+    const size_t p = (size_t)i + (size_t)nx * j;
+    if (FROM_RES) return point_residual(u, f, nx, p, k);
+    return u[p];
+}
+
+template <bool FROM_RES>
+__device__ __forceinline__ double coarse_value(const double *__restrict__ u, const double *__restrict__ f, int nx, int I, int J,
+                                               int nxc, int nyc, bool fw, const Coef &k)
+{
+    if (I < 1 || I > nxc - 2 || J < 1 || J > nyc - 2) return 0.0;
+    const int i = 2 * I, j = 2 * J;
+    if (!fw) return fine_value<FROM_RES>(u, f, nx, i, j, k);
+    const double corners = (fine_value<FROM_RES>(u, f, nx, i - 1, j - 1, k) + fine_value<FROM_RES>(u, f, nx, i + 1, j - 1, k)) +
+                           (fine_value<FROM_RES>(u, f, nx, i - 1, j + 1, k) + fine_value<FROM_RES>(u, f, nx, i + 1, j + 1, k));
+    const double edges = (fine_value<FROM_RES>(u, f, nx, i - 1, j, k) + fine_value<FROM_RES>(u, f, nx, i + 1, j, k)) +
+                         (fine_value<FROM_RES>(u, f, nx, i, j - 1, k) + fine_value<FROM_RES>(u, f, nx, i, j + 1, k));
+    return ((corners + 2.0 * edges) + 4.0 * fine_value<FROM_RES>(u, f, nx, i, j, k)) * 0.0625;
+}
+
+__global__ void __launch_bounds__(256) mg_restrict_kernel(const RestrictArgs a)
+{
+    const double *u = a.u;
+    const double *rhs = a.rhs;
+    double h = a.h, c = a.c;
+    int apply_bcs = a.apply_bcs;
+    if (a.cp != nullptr) {
+        c = a.cp->c;
+        h = level_h(a.cp, a.level);
+        apply_bcs = a.cp->apply_bcs;
+        if (a.level == 0) { u = a.cp->u; rhs = a.cp->rhs; }
+    }
+    const Coef k = make_coef(h, c, 1.0);
+    const int I = blockIdx.x * 64 + threadIdx.x, J = blockIdx.y * 4 + threadIdx.y;
+    if (I >= a.nxc || J >= a.nyc) return;
+    int Is = I;
+    if (apply_bcs) {  // coarse[0,:] = coarse[1,:]; coarse[nxc-1,:] = coarse[nxc-2,:]   part2_utils.jl:34-39
+        if (I == 0) Is = 1;
+        else if (I == a.nxc - 1) Is = a.nxc - 2;
+    }
+    const bool fw = a.full_weighting != 0;
+    const double v = a.from_res ? coarse_value<true>(u, rhs, a.nx, Is, J, a.nxc, a.nyc, fw, k)
+                                : coarse_value<false>(u, rhs, a.nx, Is, J, a.nxc, a.nyc, fw, k);
+    a.coarse[(size_t)I + (size_t)a.nxc * J] = v;
+    if (a.zero_out != nullptr) a.zero_out[(size_t)I + (size_t)a.nxc * J] = 0.0;
+}
+
+// Bilinear prolongation as a gather. ec's boundary ring is treated as zero (the reference scatters from interior
+// coarse points only); the summation order per fine point is the arrival order of the reference's CPU loop.
+__device__ __forceinline__ double coarse_at(const double *__restrict__ ec, int nxc, int nyc, int I, int J)
+{
+    return (I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2) ? ec[(size_t)I + (size_t)nxc * J] : 0.0;
+}
+__device__ __forceinline__ double prolong_value(const double *__restrict__ ec, int nxc, int nyc, int i, int j)
+{
+    const int I = i >> 1, J = j >> 1;
+    const bool io = i & 1, jo = j & 1;
+    if (!io && !jo) return coarse_at(ec, nxc, nyc, I, J);
+    if (io && !jo) return 0.5 * coarse_at(ec, nxc, nyc, I, J) + 0.5 * coarse_at(ec, nxc, nyc, I + 1, J);
+    if (!io && jo) return 0.5 * coarse_at(ec, nxc, nyc, I, J) + 0.5 * coarse_at(ec, nxc, nyc, I, J + 1);
+    return ((0.25 * coarse_at(ec, nxc, nyc, I, J) + 0.25 * coarse_at(ec, nxc, nyc, I + 1, J)) +
+            0.25 * coarse_at(ec, nxc, nyc, I, J + 1)) + 0.25 * coarse_at(ec, nxc, nyc, I + 1, J + 1);
+}
+__device__ __forceinline__ double prolong_value_bc(const double *__restrict__ ec, int nxc, int nyc, int nx, int i, int j,
+                                                   int apply_bcs)
+{
+    if (apply_bcs) {  // fine[0,:] = fine[1,:]; fine[nx-1,:] = fine[nx-2,:]
+        if (i == 0) i = 1;
+        else if (i == nx - 1) i = nx - 2;
+    }
+    return prolong_value(ec, nxc, nyc, i, j);
+}
+
+struct ProlongArgs {
+    const MGCall *cp;
+    int level;            // fine level
+    const double *coarse;
+    double *fine;         // mode 0: fine = P(coarse) ; mode 1: fine = fine - P(coarse)
+    int nx, ny, nxc, nyc, rows;
+    int mode, apply_bcs;
+};
+
+__global__ void __launch_bounds__(kMGBX) mg_prolong_kernel(const ProlongArgs a)
+{
+    double *fine = a.fine;
+    int apply_bcs = a.apply_bcs;
+    if (a.cp != nullptr) {
+        apply_bcs = a.cp->apply_bcs;
+        if (a.level == 0) fine = a.cp->u;
+    }
+    const int i = blockIdx.x * kMGBX + threadIdx.x;
+    if (i >= a.nx) return;
+    const int j0 = blockIdx.y * a.rows, j1 = min(j0 + a.rows, a.ny);
+    for (int j = j0; j < j1; ++j) {
+        const size_t p = (size_t)i + (size_t)a.nx * j;
+        const double e = prolong_value_bc(a.coarse, a.nxc, a.nyc, a.nx, i, j, apply_bcs);
+        fine[p] = a.mode == 0 ? e : fine[p] - e;  // u_f .= u_f - corr_f   multigrid.jl:139
+    }
+}
+
+// Fused prolongation + correction + first post-smoothing Jacobi sweep:
+//   out = J(u - P(ec)),  and the corrected frame is carried over.  Same arithmetic as the three separate steps.
+struct ProlongSmoothArgs {
+    const MGCall *cp;
+    int level;
+    const double *coarse;
+    const double *u;    // fine unknown before correction
+    const double *rhs;
+    double *out;
+    int nx, ny, nxc, nyc, rows;
+};
+
+__global__ void __launch_bounds__(kMGBX) mg_prolong_smooth_kernel(const ProlongSmoothArgs a)
+{
+    const double *u = a.u;
+    const double *rhs = a.rhs;
+    const MGCall *cp = a.cp;
+    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int i = blockIdx.x * kMGBX + threadIdx.x;
+    if (i >= nx) return;
+    const int j0 = blockIdx.y * a.rows, j1 = min(j0 + a.rows, ny);
+    auto corrected = [&](int ii, int jj) {
+        return u[(size_t)ii + (size_t)nx * jj] - prolong_value_bc(a.coarse, nxc, nyc, nx, ii, jj, apply_bcs);
+    };
+    const bool xin = i >= 1 && i <= nx - 2;
+    for (int j = j0; j < j1; ++j) {
+        const size_t p = (size_t)i + (size_t)nx * j;
+        const double uc = corrected(i, j);
+        if (xin && j >= 1 && j <= ny - 2) {
+            const double r = ((corrected(i + 1, j) + corrected(i - 1, j) + corrected(i, j + 1) + corrected(i, j - 1) - k.C * uc) *
+                                  k._h2 - rhs[p]);
+            a.out[p] = uc + k.w * r;
+        } else {
+            a.out[p] = uc;
+        }
+    }
+}
+
+// apply_boundary_conditions!(T): Dirichlet T[:,0]=1, T[:,ny-1]=0, then Neumann T[0,:]=T[1,:], T[nx-1,:]=T[nx-2,:]
+// (part2_utils.jl:21-39). kind: 0 both, 1 Dirichlet only, 2 Neumann only.
+__global__ void mg_bc_kernel(const MGCall *cp, double *T, int nx, int ny, int kind)
+{
+    if (cp != nullptr) {
+        if (!cp->bc_before) return;
+        T = cp->u;
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool dir = kind == 0 || kind == 1, neu = kind == 0 || kind == 2;
+    if (t < nx) {  // y edges; x-corners are finalised by the Neumann part below
+        const int i = t;
+        const bool corner = (i == 0 || i == nx - 1);
+        if (dir && !(neu && corner)) {
+            T[(size_t)i] = 1.0;
+            T[(size_t)i + (size_t)nx * (ny - 1)] = 0.0;
+        }
+    } else if (t < nx + ny) {
+        const int j = t - nx;
+        if (neu) {
+            double lo, hi;
+            if (dir && j == 0) { lo = 1.0; hi = 1.0; }
+            else if (dir && j == ny - 1) { lo = 0.0; hi = 0.0; }
+            else { lo = T[(size_t)1 + (size_t)nx * j]; hi = T[(size_t)(nx - 2) + (size_t)nx * j]; }
+            T[(size_t)nx * j] = lo;
+            T[(size_t)(nx - 1) + (size_t)nx * j] = hi;
+        }
+    }
+}
+
+// (lap - c) T with separate hx, hy, true divisions (krylov.jl:7-13). Interior only.
+__global__ void __launch_bounds__(kMGBX) mg_matvec_kernel(const double *__restrict__ T, double hx, double hy, double c,
+                                                          double *__restrict__ out, int nx, int ny, int rows)
+{
+    const int i = blockIdx.x * kMGBX + threadIdx.x;
+    if (i < 1 || i > nx - 2) return;
+    const int j0 = max(1, blockIdx.y * rows), j1 = min(blockIdx.y * rows + rows, ny - 1);
+    for (int j = j0; j < j1; ++j) {
+        const size_t p = (size_t)i + (size_t)nx * j;
+        out[p] = ((T[p + 1] - 2 * T[p] + T[p - 1]) / (hx * hx) + (T[p + nx] - 2 * T[p] + T[p - nx]) / (hy * hy)) - c * T[p];
+    }
+}
+
+// Deterministic reductions / vector updates of cg! and of the residual checks.
+// op 0: sum x*y ; op 1: sum x*x.  Fixed grid (kReduceBlocks) -> fixed summation order.
+constexpr int kReduceBlocks = 296, kReduceThreads = 256;
+__global__ void __launch_bounds__(kReduceThreads) mg_reduce_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                                                  size_t n, double *partials, unsigned int *ticket,
+                                                                  double *out, const MGCall *cp, int use_cp_rhs)
+{
+    __shared__ double red[32];
+    if (use_cp_rhs) { x = cp->rhs; y = cp->rhs; }
+    double acc = 0.0;
+    for (size_t p = (size_t)blockIdx.x * kReduceThreads + threadIdx.x; p < n; p += (size_t)kReduceBlocks * kReduceThreads)
+        acc += x[p] * y[p];
+    const double bsum = block_sum(acc, red);
+    double total;
+    if (grid_sum_last_block(bsum, partials, ticket, gridDim.x, blockIdx.x, red, &total)) *out = total;
+}
+// op 0: y += alpha*x ; op 1: y = x + beta*y ; op 2: y = y - x ; op 3: y[0] = y[2] + y[3] (red + black partial sums)
+__global__ void mg_axpy_kernel(double s, const double *__restrict__ x, double *__restrict__ y, size_t n, int op)
+{
+    if (op == 3) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) y[0] = y[2] + y[3];
+        return;
+    }
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        if (op == 0) y[p] += s * x[p];
+        else if (op == 1) y[p] = x[p] + s * y[p];
+        else y[p] = y[p] - x[p];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Collapsed coarse hierarchy: every level that fits into shared memory is processed by ONE thread block -- the
+// remaining restrict / smooth / coarsest solve / prolongate chain of the V-cycle without a single kernel launch or
+// host synchronisation in between. The data-dependent coarsest solve (<= 20*cs Jacobi sweeps with the reference's
+// exit test, or CG) runs inside one warp when the grid is tiny, so its ~50-100 dependent sweeps cost __syncwarp()s.
+// ---------------------------------------------------------------------------------------------------------------
+struct CoarseArgs {
+    const MGCall *cp;
+    int level0;               // global level index of the first shared-memory level
+    int nlev;                 // number of shared-memory levels (>= 1); the last one is the coarsest
+    int nx[kMaxLevels], ny[kMaxLevels];
+    const double *rhs_in;     // global rhs of level0 (nullptr: cp->rhs, i.e. level0 == 0)
+    double *u_io;             // global unknown of level0 (nullptr: cp->u)
+    int u_is_input;           // 1: start from the values in u_io (top-level coarsest solve); 0: start from zero
+    int coarse_solve_size, coarse_solver, smoother, restriction;
+    double *sumsq_out;        // nullable: sum res^2 of the last sweep when level0 == 0 has no finer level
+};
+
+struct BlockGroup {
+    double *red;
+    __device__ __forceinline__ int rank() const { return threadIdx.x; }
+    __device__ __forceinline__ int size() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ double sum(double v) const
+    {
+        double r = block_sum(v, red);
+        __shared__ double bc;
+        if (threadIdx.x == 0) bc = r;
+        __syncthreads();
+        r = bc;
+        __syncthreads();
+        return r;
+    }
+};
+struct WarpGroup {
+    __device__ __forceinline__ int rank() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int size() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ double sum(double v) const { return warp_sum(v); }
+};
+
+template <class G>
+__device__ __forceinline__ void sm_fill(const G &g, double *a, int n, double v)
+{
+    for (int p = g.rank(); p < n; p += g.size()) a[p] = v;
+}
+
+// out = u + w*res(u) (frame copied); returns sum res^2 if want_norm (valid on every thread of the group)
+template <class G>
+__device__ __forceinline__ double sm_jacobi(const G &g, const double *u, const double *rhs, double *out, int nx, int ny,
+                                            const Coef &k, bool want_norm)
+{
+    double acc = 0.0;
+    const int n = nx * ny;
+    for (int p = g.rank(); p < n; p += g.size()) {
+        const int i = p % nx, j = p / nx;
+        if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
+            const double r = ((u[p + 1] + u[p - 1] + u[p + nx] + u[p - nx] - k.C * u[p]) * k._h2 - rhs[p]);
+            acc += r * r;
+            out[p] = u[p] + k.w * r;
+        } else {
+            out[p] = u[p];
+        }
+    }
+    double tot = 0.0;
+    if (want_norm) tot = g.sum(acc);
+    g.sync();
+    return tot;
+}
+
+// in-place red-black Gauss-Seidel sweep; returns (sum red) + (sum black) of the pre-update res^2
+template <class G>
+__device__ __forceinline__ double sm_rbgs(const G &g, double *u, const double *rhs, int nx, int ny, double h, double c,
+                                          bool want_norm)
+{
+    const double C = 4.0 + c * (h * h), h2 = h * h, w = 1.0 * (h2 / C);
+    double tot = 0.0;
+    const int n = nx * ny;
+    for (int colour = 0; colour < 2; ++colour) {
+        double acc = 0.0;
+        for (int p = g.rank(); p < n; p += g.size()) {
+            const int i = p % nx, j = p / nx;
+            if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2 && ((i + j + colour) & 1) == 0) {
+                const double r = (u[p + 1] + u[p - 1] + u[p + nx] + u[p - nx] - C * u[p]) / h2 - rhs[p];
+                u[p] = u[p] + w * r;
+                acc += r * r;
+            }
+        }
+        if (want_norm) tot += g.sum(acc);
+        g.sync();
+    }
+    return tot;
+}
+
+template <class G>
+__device__ __forceinline__ double sm_sumsq(const G &g, const double *a, int n)
+{
+    double acc = 0.0;
+    for (int p = g.rank(); p < n; p += g.size()) acc += a[p] * a[p];
+    return g.sum(acc);
+}
+template <class G>
+__device__ __forceinline__ double sm_dot(const G &g, const double *a, const double *b, int n)
+{
+    double acc = 0.0;
+    for (int p = g.rank(); p < n; p += g.size()) acc += a[p] * b[p];
+    return g.sum(acc);
+}
+
+// cg!(x_in, b, hx, hy, c, tol, Nmax)  krylov.jl:55-91.  work = 4*n doubles (r, p, ph, x). Returns sum r^2.
+template <class G>
+__device__ __forceinline__ double sm_cg(const G &g, double *x_in, const double *b, double *work, int nx, int ny, double hx,
+                                        double hy, double c, double tol, int Nmax, int *iters_out)
+{
+    const int n = nx * ny;
+    double *r = work, *p = work + n, *ph = work + 2 * n, *x = work + 3 * n;
+    const double normb = sqrt(sm_sumsq(g, b, n));
+    const double tolb = tol * normb;
+    for (int q = g.rank(); q < n; q += g.size()) { r[q] = b[q]; p[q] = b[q]; ph[q] = b[q]; x[q] = 0.0; }
+    g.sync();
+    double rho = sm_dot(g, r, r, n);
+    int it = 0;
+    for (int k = 1; k <= Nmax; ++k) {
+        it = k;
+        for (int q = g.rank(); q < n; q += g.size()) {
+            const int i = q % nx, j = q / nx;
+            if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2)
+                ph[q] = ((p[q + 1] - 2 * p[q] + p[q - 1]) / (hx * hx) + (p[q + nx] - 2 * p[q] + p[q - nx]) / (hy * hy)) - c * p[q];
+        }
+        g.sync();
+        const double alpha = rho / sm_dot(g, p, ph, n);
+        for (int q = g.rank(); q < n; q += g.size()) { x[q] += alpha * p[q]; r[q] -= alpha * ph[q]; }
+        g.sync();
+        const double rr = sm_sumsq(g, r, n);
+        if (sqrt(rr) < tolb) break;
+        const double rho_old = rho;
+        rho = rr;
+        const double beta = rho / rho_old;
+        for (int q = g.rank(); q < n; q += g.size()) p[q] = r[q] + beta * p[q];
+        g.sync();
+    }
+    for (int q = g.rank(); q < n; q += g.size()) x_in[q] = x[q];
+    g.sync();
+    if (iters_out != nullptr && g.rank() == 0) *iters_out = it;
+    return sm_sumsq(g, r, n);
+}
+
+// Coarsest-level solve (multigrid.jl:145-167). u in place; tmp = scratch of the level; work = CG scratch.
+template <class G>
+__device__ __forceinline__ double sm_coarsest(const G &g, double *u, const double *rhs, double *tmp, double *work, int nx,
+                                              int ny, double h, const CoarseArgs &a, double c, double tol, int *sweeps_out)
+{
+    const int iters = 20 * a.coarse_solve_size;
+    const int n = nx * ny;
+    double ss = 0.0;
+    if (a.coarse_solver == B2S_COARSE_JACOBI) {
+        const double tol_rhs = tol * sqrt(sm_sumsq(g, rhs, n) / ((double)nx * ny));
+        const Coef k = make_coef(h, c, 4.0 / 5.0);
+        int sweeps = 0;
+        double *src = u, *dst = tmp;
+        for (int s = 1; s <= iters; ++s) {
+            if (a.smoother == B2S_SMOOTH_RBGS) {
+                ss = sm_rbgs(g, u, rhs, nx, ny, h, c, true);
+            } else {
+                ss = sm_jacobi(g, src, rhs, dst, nx, ny, k, true);
+                double *t = src; src = dst; dst = t;
+            }
+            ++sweeps;
+            if (sqrt(ss / ((double)nx * ny)) < tol_rhs) break;
+        }
+        if (src != u) {  // odd number of Jacobi sweeps: result sits in tmp
+            for (int p = g.rank(); p < n; p += g.size()) u[p] = src[p];
+            g.sync();
+        }
+        if (sweeps_out != nullptr && g.rank() == 0) *sweeps_out = sweeps;
+    } else {
+        ss = sm_cg(g, u, rhs, work, nx, ny, h, h, c, tol, iters, sweeps_out);
+    }
+    return ss;
+}
+
+__global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
+{
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    const MGCall *cp = a.cp;
+    const double c = cp->c, tol = cp->tol;
+    const int apply_bcs = cp->apply_bcs;
+    const bool fw = a.restriction == B2S_RESTRICT_FW;
+    BlockGroup bg{red};
+    // carve shared memory: per level u, rhs, tmp; then CG scratch for the coarsest
+    double *U[kMaxLevels], *F[kMaxLevels], *T[kMaxLevels];
+    {
+        double *ptr = sm;
+        for (int l = 0; l < a.nlev; ++l) {
+            const int n = a.nx[l] * a.ny[l];
+            U[l] = ptr; ptr += n;
+            F[l] = ptr; ptr += n;
+            T[l] = ptr; ptr += n;
+        }
+        U[a.nlev] = ptr;  // CG scratch (4 * n_coarsest)
+    }
+    const double *rhs_g = a.rhs_in != nullptr ? a.rhs_in : cp->rhs;
+    double *u_g = a.u_io != nullptr ? a.u_io : cp->u;
+    {
+        const int n = a.nx[0] * a.ny[0];
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            F[0][p] = rhs_g[p];
+            U[0][p] = a.u_is_input ? u_g[p] : 0.0;
+        }
+        __syncthreads();
+    }
+    double last_ss = 0.0;
+    // ---- downward leg ---------------------------------------------------------------------------------------
+    for (int l = 0; l + 1 < a.nlev; ++l) {
+        const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
+        const double h = level_h(cp, a.level0 + l);
+        const Coef k = make_coef(h, c, 4.0 / 5.0);
+        if (a.smoother == B2S_SMOOTH_RBGS) {
+            sm_rbgs(bg, U[l], F[l], nx, ny, h, c, false);
+            sm_rbgs(bg, U[l], F[l], nx, ny, h, c, false);
+        } else {
+            sm_jacobi(bg, U[l], F[l], T[l], nx, ny, k, false);
+            sm_jacobi(bg, T[l], F[l], U[l], nx, ny, k, false);
+        }
+        const Coef kr = make_coef(h, c, 1.0);
+        for (int p = threadIdx.x; p < nxc * nyc; p += blockDim.x) {
+            int I = p % nxc;
+            const int J = p / nxc;
+            if (apply_bcs) {
+                if (I == 0) I = 1;
+                else if (I == nxc - 1) I = nxc - 2;
+            }
+            F[l + 1][p] = coarse_value<true>(U[l], F[l], nx, I, J, nxc, nyc, fw, kr);
+            U[l + 1][p] = 0.0;
+        }
+        __syncthreads();
+    }
+    // ---- coarsest solve ---------------------------------------------------------------------------------------
+    {
+        const int l = a.nlev - 1;
+        const int nx = a.nx[l], ny = a.ny[l];
+        const double h = level_h(cp, a.level0 + l);
+        if (nx * ny <= 1024) {
+            if (threadIdx.x < 32) {
+                WarpGroup wg;
+                last_ss = sm_coarsest(wg, U[l], F[l], T[l], U[a.nlev], nx, ny, h, a, c, tol, cp->coarse_sweeps);
+            }
+            __syncthreads();
+        } else {
+            last_ss = sm_coarsest(bg, U[l], F[l], T[l], U[a.nlev], nx, ny, h, a, c, tol, cp->coarse_sweeps);
+        }
+    }
+    // ---- upward leg -------------------------------------------------------------------------------------------
+    for (int l = a.nlev - 2; l >= 0; --l) {
+        const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
+        const double h = level_h(cp, a.level0 + l);
+        const Coef k = make_coef(h, c, 4.0 / 5.0);
+        for (int p = threadIdx.x; p < nx * ny; p += blockDim.x) {
+            const int i = p % nx, j = p / nx;
+            U[l][p] = U[l][p] - prolong_value_bc(U[l + 1], nxc, nyc, nx, i, j, apply_bcs);
+        }
+        __syncthreads();
+        const bool top = (l == 0 && a.sumsq_out != nullptr);
+        if (a.smoother == B2S_SMOOTH_RBGS) {
+            sm_rbgs(bg, U[l], F[l], nx, ny, h, c, false);
+            last_ss = sm_rbgs(bg, U[l], F[l], nx, ny, h, c, top);
+        } else {
+            sm_jacobi(bg, U[l], F[l], T[l], nx, ny, k, false);
+            last_ss = sm_jacobi(bg, T[l], F[l], U[l], nx, ny, k, top);
+        }
+    }
+    {
+        const int n = a.nx[0] * a.ny[0];
+        for (int p = threadIdx.x; p < n; p += blockDim.x) u_g[p] = U[0][p];
+        if (a.sumsq_out != nullptr && threadIdx.x == 0) *a.sumsq_out = last_ss;
+    }
+}
+
+// Stand-alone CG for grids that fit into shared memory (test/krylov.jl shape: 66^2).
+__global__ void __launch_bounds__(1024) mg_cg_smem_kernel(double *x, const double *b, double hx, double hy, double c, double tol,
+                                                          int nmax, int nx, int ny, double *ss_out, int *iters_out)
+{
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    BlockGroup bg{red};
+    const int n = nx * ny;
+    double *bs = sm, *xs = sm + n, *work = sm + 2 * n;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) { bs[p] = b[p]; xs[p] = x[p]; }
+    __syncthreads();
+    const double ss = sm_cg(bg, xs, bs, work, nx, ny, hx, hy, c, tol, nmax, iters_out);
+    for (int p = threadIdx.x; p < n; p += blockDim.x) x[p] = xs[p];
+    if (threadIdx.x == 0) *ss_out = ss;
+}
+
+}  // namespace b2s

@@ -107,6 +107,8 @@ typedef struct {
 int b2s_diff3d_create(b2s_diff3d **h, const b2s_diff3d_config *cfg);
 int b2s_diff3d_destroy(b2s_diff3d *h);
 int b2s_diff3d_get_params(const b2s_diff3d *h, b2s_diff3d_params *out);
+/* Same numbers without a handle or a GPU (pure host arithmetic; used to size host buffers before create). */
+int b2s_diff3d_params_for(const b2s_diff3d_config *cfg, b2s_diff3d_params *out);
 
 /* Ht = init_local_gaussian; apply_boundary_conditions!; Htau = copy(Ht); Htau2 = 0
  * (part1_kernel_programming.jl:137-142, part1_utils.jl:1-34). Evaluated on the host like the reference. */

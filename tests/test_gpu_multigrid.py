@@ -1,0 +1,283 @@
+"""GPU parity of hot path 2 (2-D multigrid V-cycle, CG, Navier-Stokes step) against the CPU oracle, through the C ABI.
+
+Bar: fields bit-exact (same operation order, -fmad=false vs -ffp-contract=off) unless a reduction decides control flow
+at a knife edge; norms within 1e-12 relative (different summation order); identical V-cycle and sweep counts.
+Reference: scripts-part2/multigrid.jl, krylov.jl, part2.jl, part2_utils.jl; test/multigrid.jl, test/krylov.jl,
+test/part2.jl."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+F = os.path.join(GOLDEN, "fortran")
+RTOL_NORM = 1e-12
+
+
+@pytest.fixture(scope="module")
+def p2(b2s, gpu):
+    from b200stencil import part2
+    return part2
+
+
+def rnd(shape, seed):
+    return np.asfortranarray(np.random.default_rng(seed).random(shape))
+
+
+@pytest.mark.parametrize("shape", [(33, 33), (65, 17), (64, 64), (129, 257), (300, 7)])
+def test_l0_residual_iteration_matvec(p2, oracle, shape):
+    nx, ny = shape
+    h, c = 1.0 / (ny - 1), 3.1415
+    u, f = rnd(shape, 1), rnd(shape, 2)
+    du, df, dres = p2.to_device(u), p2.to_device(f), p2.to_device(rnd(shape, 3))
+    res0 = p2.to_host(dres)
+    p2.residual_2DPoisson_wrapper(du, df, h, c, dres, p2.parallel)
+    ro = oracle.residual2d(u, f, h, c)
+    got = p2.to_host(dres)
+    assert np.array_equal(got[1:-1, 1:-1], ro[1:-1, 1:-1])
+    assert np.array_equal(got[0, :], res0[0, :]) and np.array_equal(got[:, -1], res0[:, -1])  # frame untouched
+    # iteration_2DPoisson! (in place, r_rms pre-update)
+    dres.zero_()
+    uo, reso = u.copy(order="F"), oracle.farray(shape)
+    r_o = oracle.jacobi2d(uo, f, h, c, reso)
+    r_g = p2.iteration_2DPoisson(du, df, h, c, dres, p2.parallel_shmem)
+    assert abs(r_g - r_o) <= RTOL_NORM * r_o
+    assert np.array_equal(p2.to_host(du), uo) and np.array_equal(p2.to_host(dres), reso)
+    # matvec with hx != hy
+    dout = p2.to_device(rnd(shape, 4))
+    out0 = p2.to_host(dout)
+    p2.matrix_free_matvec_prod_wrapper(p2.to_device(u), 0.01, 0.02, c, dout)
+    mo = oracle.matvec2d(u, 0.01, 0.02, c, out0.copy(order="F"))
+    assert np.array_equal(p2.to_host(dout), mo)
+
+
+@pytest.mark.parametrize("shape", [(33, 33), (65, 17), (9, 129)])
+@pytest.mark.parametrize("bcs", [False, True])
+def test_l0_transfer_operators(p2, oracle, shape, bcs):
+    nx, ny = shape
+    cshape = (1 + (nx - 1) // 2, 1 + (ny - 1) // 2)
+    fine = rnd(shape, 5)
+    dc = p2.to_device(rnd(cshape, 6))
+    p2.restrict_wrapper(p2.to_device(fine), dc, bcs)
+    assert np.array_equal(p2.to_host(dc), oracle.restrict_inject(fine, bcs))
+    p2.restrict_wrapper(p2.to_device(fine), dc, bcs, full_weighting=True)
+    assert np.array_equal(p2.to_host(dc), oracle.restrict_fw(fine, bcs))
+    coarse = rnd(cshape, 7)  # non-zero boundary ring: must be ignored like in the reference scatter
+    df = p2.to_device(rnd(shape, 8))
+    p2.prolongate_wrapper(p2.to_device(coarse), df, bcs)
+    assert np.array_equal(p2.to_host(df), oracle.prolongate(coarse, shape, bcs))
+
+
+def test_l0_bcs_reductions_axpy_rbgs(p2, oracle):
+    from b200stencil import capi
+    shape = (37, 21)
+    T = rnd(shape, 9)
+    for fn_g, fn_o in ((p2.apply_boundary_conditions, "orc_bc_apply"), (p2.apply_boundary_conditions_dirichlet, "orc_bc_dirichlet"),
+                       (p2.apply_boundary_conditions_neumann, "orc_bc_neumann")):
+        d = p2.to_device(T)
+        fn_g(d)
+        To = T.copy(order="F")
+        getattr(oracle.lib(), fn_o)(oracle._p(To), *shape)
+        assert np.array_equal(p2.to_host(d), To), fn_o
+    x, y = rnd((513, 257), 10), rnd((513, 257), 11)
+    dx, dy = p2.to_device(x), p2.to_device(y)
+    assert abs(p2.dot(dx, dy) - float(np.sum(x * y))) <= 1e-12 * np.sum(x * y)
+    assert abs(p2.sumsq(dx) - float(np.sum(x * x))) <= 1e-12 * np.sum(x * x)
+    L = capi.lib()
+    capi.check(L.b2s_axpy(0.37, capi.ptr(dx), capi.ptr(dy), x.size, None))
+    assert np.array_equal(p2.to_host(dy), y + 0.37 * x)
+    capi.check(L.b2s_xpby(capi.ptr(dx), -1.25, capi.ptr(dy), x.size, None))
+    assert np.array_equal(p2.to_host(dy), x + (-1.25) * (y + 0.37 * x))
+    # variant-B smoother
+    shape = (65, 33)
+    u, f = rnd(shape, 12), rnd(shape, 13)
+    du = p2.to_device(u)
+    r_g = p2.rbgs_2DPoisson(du, p2.to_device(f), 1.0 / 32, 0.7)
+    uo = u.copy(order="F")
+    r_o = oracle.rbgs2d(uo, f, 1.0 / 32, 0.7)
+    assert np.array_equal(p2.to_host(du), uo) and abs(r_g - r_o) <= RTOL_NORM * r_o
+
+
+CONFIGS = [
+    dict(),                                             # defaults: graph + collapsed coarse levels, cs=5, Jacobi
+    dict(use_graph=False),
+    dict(smem_levels=False),
+    dict(coarse_solve_size=9),
+    dict(coarse_solver=1),                              # CG coarse solver
+    dict(coarse_solve_size=9, coarse_solver=1, use_graph=False),
+    dict(smoother=1, restriction=1),                    # variant B: RB-GS + full weighting
+    dict(smoother=1, restriction=1, use_graph=False, smem_levels=False),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[str(c) for c in CONFIGS])
+@pytest.mark.parametrize("shape,c,bcs", [((129, 129), 0.0, False), ((257, 65), 123.4, True), ((65, 257), 0.0, False),
+                                         ((513, 513), 5.0e3, True)])
+def test_vcycle_matches_oracle(p2, oracle, cfg, shape, c, bcs):
+    nx, ny = shape
+    h = 1.0 / (min(nx, ny) - 1)
+    opt_g = p2.MGOpt(**cfg)
+    opt_o = oracle.MGOpt(coarse_solve_size=cfg.get("coarse_solve_size", 5), coarse_solver=cfg.get("coarse_solver", 0),
+                         smoother=cfg.get("smoother", 0), restriction=cfg.get("restriction", 0))
+    u, f = rnd(shape, 21), rnd(shape, 22)
+    hd = p2.preallocate_buffers(nx, ny, opt_g)
+    du, df = p2.to_device(u), p2.to_device(f)
+    uo = u.copy(order="F")
+    for cyc in range(2):
+        r_o = oracle.vcycle2d(uo, f, h, c, 1e-6, bcs, opt_o)
+        sw_o = oracle.lib().orc_mg_last_coarse_sweeps()
+        r_g = hd.vcycle(du, df, h, c, 1e-6, bcs)
+        assert hd.last_coarse_sweeps() == sw_o, cyc
+        assert abs(r_g - r_o) <= 1e-11 * r_o, cyc
+        got = p2.to_host(du)
+        if cfg.get("coarse_solver", 0) == 1:  # CG: alpha/beta come from reductions -> last-bit differences
+            assert np.max(np.abs(got - uo)) <= 1e-11 * np.max(np.abs(uo)), cyc
+        else:
+            assert np.array_equal(got, uo), cyc
+    hd.close()
+
+
+@pytest.mark.parametrize("n,cs,solver", [(129, 5, 0), (129, 9, 1), (257, 5, 0), (1025, 5, 0), (1025, 9, 0), (1025, 5, 1)])
+def test_mgsolve_bench_shape_counts(p2, oracle, n, cs, solver):
+    """multigrid_bench.jl shape (config #2): 7 V-cycles; result equal to the oracle's."""
+    h = 1.0 / (n - 1)
+    b = rnd((n, n), 1)
+    xo = oracle.farray((n, n))
+    r_o, nc_o, hist_o = oracle.mgsolve2d(xo, b, h, 0.0, 1e-6, 100, opt=oracle.MGOpt(coarse_solve_size=cs, coarse_solver=solver))
+    x = p2.zeros(n, n)
+    hd = p2.preallocate_buffers(n, n, p2.MGOpt(coarse_solve_size=cs, coarse_solver=solver))
+    r_g, nc_g, hist_g = hd.solve(x, p2.to_device(b), h, 0.0, 1e-6, 100, False, want_hist=True)
+    assert nc_g == nc_o == 7
+    assert np.allclose(hist_g, hist_o, rtol=1e-9, atol=0)
+    assert r_g < 1e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
+    got = p2.to_host(x)
+    if solver == 0:
+        assert np.array_equal(got, xo)
+    else:
+        assert np.max(np.abs(got - xo)) <= 1e-11 * np.max(np.abs(xo))
+    hd.close()
+
+
+def test_variant_b_five_cycles(p2, oracle):
+    n = 1025
+    b = rnd((n, n), 1)
+    x = p2.zeros(n, n)
+    r, nc = p2.MGsolve_2DPoisson(x, p2.to_device(b), 1.0 / (n - 1), 0.0, 1e-6, 30, False,
+                                 opt=p2.MGOpt(smoother=1, restriction=1), return_cycles=True)
+    xo = oracle.farray((n, n))
+    r_o, nc_o, _ = oracle.mgsolve2d(xo, b, 1.0 / (n - 1), 0.0, 1e-6, 30, opt=oracle.MGOpt(smoother=1, restriction=1))
+    assert nc == nc_o == 5
+    assert np.array_equal(p2.to_host(x), xo)
+
+
+def test_fortran_golden_poisson_and_explicit_step(p2, oracle):
+    """test/part2.jl: navier_stokes_2D(testmode) at 257x65, tol 1e-12, W from Winit.bin vs {T,W,S}.bin, atol 1e-8."""
+    Winit = p2.load(os.path.join(F, "Winit.bin"))
+    opt = p2.SimIn_t(nx=257, ny=65, tol=1.0e-12, W_init=Winit)
+    out, infos = p2.navier_stokes_2D(opt=opt, verbose=False, testmode=True, return_infos=True)
+    assert infos[0][1] == 14 and infos[0][0] == 3.662109375e-5
+    inner = (slice(1, -1), slice(1, -1))
+    for name, arr in (("T", out.T), ("W", out.W), ("S", out.S)):
+        ref = p2.load(os.path.join(F, name + ".bin"))
+        assert arr.shape == ref.shape
+        assert np.all(np.abs(arr - ref)[inner] < 1e-8), name
+    # and bit-exact against the oracle
+    S, T, W = oracle.farray((257, 65)), oracle.ns_init_cosine(257, 65), Winit.copy(order="F")
+    oracle.ns_step(oracle.NSParams(nx=257, ny=65, tol=1e-12), S, T, W)
+    assert np.array_equal(out.S, S) and np.array_equal(out.T, T) and np.array_equal(out.W, W)
+
+
+@pytest.mark.parametrize("beta", [0.5, 1.0])
+def test_semi_implicit_steps_match_oracle(p2, oracle, beta):
+    """beta > 0 path (Helmholtz solves, apply_BCs=true) -- parity unpinned upstream, checked against the oracle."""
+    nx, ny = 257, 65
+    W0 = rnd((nx, ny), 31)
+    P = oracle.NSParams(nx=nx, ny=ny, beta=beta, Pr=0.1, tol=1e-7)
+    S, T, W = oracle.farray((nx, ny)), oracle.ns_init_cosine(nx, ny), W0.copy(order="F")
+    sim = p2.NavierStokes2D(p2.SimIn_t(nx=nx, ny=ny, beta=beta, Pr=0.1, tol=1e-7))
+    sim.init_cosine("T")
+    sim.set_field("W", W0)
+    import warnings
+    for step in range(3):
+        io, aux = oracle.ns_step(P, S, T, W, want_aux=True)
+        ig = sim.step()
+        assert (ig.cycles_S, ig.cycles_T, ig.cycles_W) == (io.cycles_S, io.cycles_T, io.cycles_W), step
+        assert ig.dt == io.dt, step
+        for name, ref in (("S", S), ("T", T), ("W", W)):
+            assert np.array_equal(sim.get_field(name), ref), (step, name)
+        for name in ("vx", "vy", "Ra_dTdx"):
+            assert np.array_equal(sim.get_aux(name), aux[name]), (step, name)
+    sim.close()
+
+
+def test_cg_reference_shape(p2, oracle):
+    """test/krylov.jl: 66^2, c = 3.14, ones with zero frame."""
+    n, c = 66, 3.14
+    h = 1.0 / (n - 1)
+    b = np.zeros((n, n), order="F"); b[1:-1, 1:-1] = 1.0
+    for policy in (p2.parallel, p2.parallel_shmem):
+        x = p2.zeros(n, n)
+        r, it = p2.cg(x, p2.to_device(b), h, h, c, 1e-6, 1000, execution_policy=policy, return_iters=True)
+        assert r < 1e-6 * np.sqrt(np.sum(b ** 2) / n ** 2)
+        xo = oracle.farray((n, n))
+        r_o, it_o = oracle.cg2d(xo, b, h, h, c, 1e-6, 1000)
+        assert it == it_o == 100
+        assert abs(r - r_o) <= 1e-6 * r_o
+        assert np.max(np.abs(p2.to_host(x) - xo)) <= 1e-9 * np.max(np.abs(xo))
+
+
+def test_jacobi_solver_like_reference_test(p2):
+    """test/multigrid.jl:60-100 on the GPU: plain damped Jacobi on 33^2 through iteration_2DPoisson."""
+    n = 33
+    h = 1.0 / (n - 1)
+    xref = np.zeros((n, n), order="F"); xref[1:-1, 1:-1] = rnd((n - 2, n - 2), 5)
+    b = np.zeros((n, n), order="F")
+    b[1:-1, 1:-1] = (xref[2:, 1:-1] + xref[:-2, 1:-1] + xref[1:-1, 2:] + xref[1:-1, :-2] - 4 * xref[1:-1, 1:-1]) / h ** 2
+    db, x, res = p2.to_device(b), p2.zeros(n, n), p2.zeros(n, n)
+    tolb = 1e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
+    for i in range(10000):
+        if p2.iteration_2DPoisson(x, db, h, 0.0, res, p2.parallel) < tolb:
+            break
+    assert np.linalg.norm(xref - p2.to_host(x)) / np.linalg.norm(xref) < tolb
+
+
+def test_error_conditions(p2):
+    from b200stencil import capi
+    with pytest.raises(capi.B2SError) as e:
+        p2.preallocate_buffers(130, 130)           # "ERROR:not a power of 2"  multigrid.jl:95-97
+    assert e.value.code == capi.ERR_BAD_SIZE
+    with pytest.raises(capi.B2SError):
+        p2.preallocate_buffers(129, 129, p2.MGOpt(coarse_solve_size=6))    # assert isinteger(log2(cs-1)) :46
+    with pytest.raises(capi.B2SError):
+        p2.preallocate_buffers(17, 17, p2.MGOpt(coarse_solve_size=33))     # assert cs <= min(nx, ny) :45
+    with pytest.raises(capi.B2SError) as e:
+        p2.residual_2DPoisson_wrapper(p2.zeros(9, 9), p2.zeros(9, 9), 0.1, 0.0, p2.zeros(9, 9), p2.serial)  # :233-236
+    assert e.value.code == capi.ERR_NOT_IMPLEMENTED
+    # non-convergence is a warning, not an error (multigrid.jl:78-82)
+    n = 129
+    x = p2.zeros(n, n)
+    with pytest.warns(UserWarning):
+        r = p2.MGsolve_2DPoisson(x, p2.to_device(rnd((n, n), 2)), 1.0 / (n - 1), 0.0, 1e-14, 2, False)
+    assert r > 0
+
+
+def test_full_size_properties(p2):
+    """2049^2 (config #4 grid) and 4097^2: graph replay == plain launches bit-for-bit, 7 V-cycles, converged."""
+    for n in (2049, 4097):
+        b = rnd((n, n), 1)
+        db = p2.to_device(b)
+        outs = []
+        for use_graph in (True, False):
+            x = p2.zeros(n, n)
+            r, nc = p2.MGsolve_2DPoisson(x, db, 1.0 / (n - 1), 0.0, 1e-6, 100, False, opt=p2.MGOpt(use_graph=use_graph),
+                                         return_cycles=True)
+            assert nc == 7 and r < 1e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
+            outs.append(p2.to_host(x))
+        assert np.array_equal(outs[0], outs[1])
+        # the discrete equation holds to the solver tolerance on the interior
+        x = outs[0]
+        lap = (x[2:, 1:-1] + x[:-2, 1:-1] + x[1:-1, 2:] + x[1:-1, :-2] - 4 * x[1:-1, 1:-1]) * (n - 1) ** 2
+        res = lap - b[1:-1, 1:-1]
+        assert np.sqrt(np.sum(res ** 2) / (n * n)) < 2e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
