@@ -1,0 +1,52 @@
+"""Multi-GPU parity of hot path 1 (needs >= 2 GPUs; skipped on a single-GPU box): z-slabs on different devices driven
+in-process, and one process per GPU with CUDA-IPC peer mappings (the layout bench.py uses under torchrun).
+Two ranks are never run on ONE GPU: their kernels wait on each other (B200_PROFILING.md)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import b200stencil  # noqa: F401
+    from b200stencil import capi
+    return capi.device_count()
+
+
+@pytest.mark.parametrize("halo_mode", [0, 1])
+def test_inprocess_two_devices_match_rank_emulation(b2s, gpu, oracle, halo_mode):
+    if gpu < 2:
+        pytest.skip("needs 2 GPUs")
+    from b200stencil import part1
+    shape, N = (64, 64, 34), 2
+    o = oracle.Diffusion3D(*shape, dims=(1, 1, N), halo_mode=halo_mode)
+    g = part1.Diffusion3D(*shape, nslabs=N, devices=[0, 1], halo_mode=halo_mode)
+    g.init_gaussian()
+    for chunk in (1, 2, 3, 30):
+        eo, eg = o.iterate(chunk), g.iterate(chunk)
+        assert np.allclose(eg, eo, rtol=1e-12, atol=0)
+        for r in range(N):
+            assert np.array_equal(g.get("Htau", r), o.get("Htau", r))
+    assert g.solve_timestep(1e-6)[0] == o.solve_timestep(1e-6)[0]
+    g.close()
+
+
+@pytest.mark.parametrize("args", [["64", "64", "34", "0", "tma"], ["32", "32", "18", "1", "direct"]])
+def test_one_process_per_gpu_matches_rank_emulation(b2s, gpu, args):
+    if gpu < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(gpu, 4)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(ROOT, "scripts", "mp_diffusion_check.py")] + args,
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for k in range(n):
+        assert f"rank{k} ok" in r.stdout
