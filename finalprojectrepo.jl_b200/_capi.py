@@ -47,7 +47,7 @@ class Diff3DParams(C.Structure):
 class MGConfig(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("coarse_solve_size", C.c_int), ("coarse_solver", C.c_int),
                 ("smoother", C.c_int), ("restriction", C.c_int), ("device", C.c_int), ("use_graph", C.c_int),
-                ("smem_levels", C.c_int)]
+                ("smem_levels", C.c_int), ("fuse_sweeps", C.c_int)]
 
 
 class NS2DParams(C.Structure):

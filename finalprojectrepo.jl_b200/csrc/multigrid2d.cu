@@ -103,8 +103,22 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         }
     };
     const int fs = h->first_smem;
+    const bool fused = c.fuse_sweeps && !rb && c.restriction == B2S_RESTRICT_INJECT;
+    auto tile_args = [&](int l) {
+        TileArgs t = {};
+        t.cp = cp; t.level = l; t.rhs = h->rhs[l]; t.nx = h->nx[l]; t.ny = h->ny[l]; t.nxc = h->nx[l + 1]; t.nyc = h->ny[l + 1];
+        t.partials = h->partials; t.ticket = h->ticket; t.sumsq_out = h->sumsq_dev;
+        return t;
+    };
+    auto tile_grid = [&](int l) { return dim3((h->nx[l] + kTW - 1) / kTW, (h->ny[l] + kTH - 1) / kTH, 1); };
     // downward leg on the global-memory levels
-    for (int l = 0; l < fs; ++l) {
+    for (int l = 0; l < fs && fused; ++l) {
+        TileArgs t = tile_args(l);
+        t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
+        mg_down_kernel<<<tile_grid(l), kTileThreads, kTileSmemBytes, st>>>(t);
+        ++n;
+    }
+    for (int l = 0; l < fs && !fused; ++l) {
         smooth2(l, false);
         RestrictArgs r = {};
         r.cp = cp; r.level = l; r.u = h->u[l]; r.rhs = h->rhs[l]; r.coarse = h->rhs[l + 1]; r.zero_out = h->u[l + 1];
@@ -129,7 +143,13 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         ++n;
     }
     // upward leg
-    for (int l = fs - 1; l >= 0; --l) {
+    for (int l = fs - 1; l >= 0 && fused; --l) {
+        TileArgs t = tile_args(l);
+        t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
+        mg_up_kernel<<<tile_grid(l), kTileThreads, kTileSmemBytes, st>>>(t);
+        ++n;
+    }
+    for (int l = fs - 1; l >= 0 && !fused; --l) {
         const int nx = h->nx[l], ny = h->ny[l];
         const int rows = rows_for(nx, ny);
         if (rb) {
@@ -327,6 +347,8 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
     MG_CUDA(cudaMalloc(&h->ticket, 64));
     MG_CUDA(cudaMemset(h->ticket, 0, 64));
     MG_CUDA(cudaFuncSetAttribute(mg_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemLimit + 1024));
+    MG_CUDA(cudaFuncSetAttribute(mg_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+    MG_CUDA(cudaFuncSetAttribute(mg_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
 #undef MG_CUDA
     *out = h;
     return B2S_OK;

@@ -327,6 +327,160 @@ __global__ void __launch_bounds__(kMGBX) mg_prolong_smooth_kernel(const ProlongS
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Temporally blocked fine-level kernels (variant A: damped Jacobi + injection). A block stages its tile of u and rhs
+// (plus a halo as wide as the number of fused steps) in shared memory and performs the WHOLE downward or upward part of
+// one level there, so a level costs two passes over HBM/L2 instead of five kernels:
+//   mg_down_kernel:  u_s = J(J(u)) ;  rc = inject(residual(u_s)) (+ Neumann) ;  ec = 0        [reads u, rhs; writes u_s, rc, ec]
+//   mg_up_kernel:    u   = J(J(u_s - P(ec))) ; sum res^2 of the last sweep                    [reads u_s, rhs, ec; writes u]
+// Every point value is produced by exactly the arithmetic of the unfused kernels (halo points are recomputed
+// redundantly by neighbouring blocks), so results are bit-identical to them.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTW = 64, kTH = 32, kTileThreads = 256;
+constexpr int kTP = kTW + 8;  // shared-memory row pitch (tile + 2*3 halo, padded)
+constexpr int kTRows = kTH + 6;
+constexpr size_t kTileSmemBytes = (size_t)3 * kTP * kTRows * sizeof(double);
+
+struct TileArgs {
+    const MGCall *cp;
+    int level;
+    const double *u_in;   // down: u_l (level 0: cp->u) ; up: smoothed u_s (tmp_l)
+    const double *rhs;    // level 0: cp->rhs
+    double *u_out;        // down: tmp_l ; up: u_l (level 0: cp->u)
+    double *rc;           // down: coarse rhs ; up: unused
+    double *ec;           // down: coarse unknown to reset ; up: coarse correction (read)
+    int nx, ny, nxc, nyc;
+    int want_norm;
+    double *partials;
+    unsigned int *ticket;
+    double *sumsq_out;
+};
+
+// one Jacobi sweep inside shared memory over the window [x0,x1) x [y0,y1) of global coordinates (clipped to the domain)
+__device__ __forceinline__ void tile_sweep(const double *__restrict__ src, const double *__restrict__ F, double *__restrict__ dst,
+                                           int gx0, int gy0, int wx0, int wy0, int W, int H, int nx, int ny, const Coef &k)
+{
+    // (gx0, gy0): global coordinates of shared-memory element (0,0); window origin (wx0, wy0), size W x H
+    for (int idx = threadIdx.x; idx < W * H; idx += kTileThreads) {
+        const int r = idx / W, c = idx - r * W;
+        const int i = wx0 + c, j = wy0 + r;
+        if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
+        const int s = (j - gy0) * kTP + (i - gx0);
+        double v = src[s];
+        if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
+            const double res = ((src[s + 1] + src[s - 1] + src[s + kTP] + src[s - kTP] - k.C * v) * k._h2 - F[s]);
+            v = v + k.w * res;
+        }
+        dst[s] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
+{
+    extern __shared__ double tsm[];
+    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
+    const MGCall *cp = a.cp;
+    const double *u = a.u_in, *rhs = a.rhs;
+    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny;
+    const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
+    const int gx0 = X0 - 3, gy0 = Y0 - 3;
+    // stage u on tile+3 and rhs on tile+2
+    for (int idx = threadIdx.x; idx < (kTW + 6) * kTRows; idx += kTileThreads) {
+        const int r = idx / (kTW + 6), c = idx - r * (kTW + 6);
+        const int i = gx0 + c, j = gy0 + r;
+        const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
+        const size_t p = (size_t)i + (size_t)nx * j;
+        A[r * kTP + c] = in ? u[p] : 0.0;
+        F[r * kTP + c] = (in && c >= 1 && c < kTW + 5 && r >= 1 && r < kTRows - 1) ? rhs[p] : 0.0;
+    }
+    __syncthreads();
+    tile_sweep(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k);
+    __syncthreads();
+    tile_sweep(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    __syncthreads();
+    // smoothed u out
+    for (int idx = threadIdx.x; idx < kTW * kTH; idx += kTileThreads) {
+        const int r = idx / kTW, c = idx - r * kTW;
+        const int i = X0 + c, j = Y0 + r;
+        if (i < nx && j < ny) a.u_out[(size_t)i + (size_t)nx * j] = A[(r + 3) * kTP + c + 3];
+    }
+    // coarse rhs = injected residual of the smoothed u (+ Neumann copies), coarse unknown = 0
+    const int nxc = a.nxc, nyc = a.nyc;
+    const Coef kr = make_coef(level_h(cp, a.level), cp->c, 1.0);
+    for (int idx = threadIdx.x; idx < (kTW / 2) * (kTH / 2); idx += kTileThreads) {
+        const int r = idx / (kTW / 2), c = idx - r * (kTW / 2);
+        const int I = X0 / 2 + c, J = Y0 / 2 + r;
+        if (I >= nxc || J >= nyc) continue;
+        const size_t pc = (size_t)I + (size_t)nxc * J;
+        a.ec[pc] = 0.0;
+        const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
+        if (interior) {
+            const int s = (2 * r + 3) * kTP + 2 * c + 3;
+            const double v = ((A[s + 1] + A[s - 1] + A[s + kTP] + A[s - kTP] - kr.C * A[s]) * kr._h2 - F[s]);
+            a.rc[pc] = v;
+            if (apply_bcs) {  // coarse[0,:] = coarse[1,:] ; coarse[nxc-1,:] = coarse[nxc-2,:]
+                if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                if (I == nxc - 2) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+            }
+        } else if (!(apply_bcs && (I == 0 || I == nxc - 1) && J >= 1 && J <= nyc - 2)) {
+            a.rc[pc] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
+{
+    extern __shared__ double tsm[];
+    __shared__ double red[32];
+    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
+    const MGCall *cp = a.cp;
+    const double *rhs = a.rhs;
+    double *out = a.u_out;
+    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
+    const int gx0 = X0 - 3, gy0 = Y0 - 3;
+    // corrected u = u_s - P(ec) on tile+2, rhs on tile+1
+    for (int idx = threadIdx.x; idx < (kTW + 4) * (kTH + 4); idx += kTileThreads) {
+        const int r = idx / (kTW + 4), c = idx - r * (kTW + 4);
+        const int i = X0 - 2 + c, j = Y0 - 2 + r;
+        const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
+        const size_t p = (size_t)i + (size_t)nx * j;
+        const int s = (r + 1) * kTP + c + 1;
+        A[s] = in ? a.u_in[p] - prolong_value_bc(a.ec, nxc, nyc, nx, i, j, apply_bcs) : 0.0;
+        F[s] = (in && c >= 1 && c < kTW + 3 && r >= 1 && r < kTH + 3) ? rhs[p] : 0.0;
+    }
+    __syncthreads();
+    tile_sweep(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    __syncthreads();
+    double acc = 0.0;
+    for (int idx = threadIdx.x; idx < kTW * kTH; idx += kTileThreads) {
+        const int r = idx / kTW, c = idx - r * kTW;
+        const int i = X0 + c, j = Y0 + r;
+        if (i >= nx || j >= ny) continue;
+        const int s = (r + 3) * kTP + c + 3;
+        double v = B[s];
+        if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
+            const double res = ((B[s + 1] + B[s - 1] + B[s + kTP] + B[s - kTP] - k.C * v) * k._h2 - F[s]);
+            acc += res * res;
+            v = v + k.w * res;
+        }
+        out[(size_t)i + (size_t)nx * j] = v;
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+    }
+}
+
 // apply_boundary_conditions!(T): Dirichlet T[:,0]=1, T[:,ny-1]=0, then Neumann T[0,:]=T[1,:], T[nx-1,:]=T[nx-2,:]
 // (part2_utils.jl:21-39). kind: 0 both, 1 Dirichlet only, 2 Neumann only.
 __global__ void mg_bc_kernel(const MGCall *cp, double *T, int nx, int ny, int kind)

@@ -138,7 +138,7 @@ int b2s_ns2d_create(b2s_ns2d **out, const b2s_ns2d_params *p, const b2s_mg_confi
     *out = nullptr;
     b2s_mg_config c;
     if (mgc) c = *mgc;
-    else { c = b2s_mg_config(); c.coarse_solve_size = 5; c.use_graph = 1; c.smem_levels = 1; }  // MGOpt() multigrid.jl:21
+    else { c = b2s_mg_config(); c.coarse_solve_size = 5; c.use_graph = 1; c.smem_levels = 1; c.fuse_sweeps = 1; }  // MGOpt() multigrid.jl:21
     c.nx = p->nx; c.ny = p->ny;
     b2s_ns2d *h = new b2s_ns2d();
     h->p = *p;

@@ -121,7 +121,7 @@ end
 
 struct MGConfig                                                 # b2s_mg_config
     nx::Cint; ny::Cint; coarse_solve_size::Cint; coarse_solver::Cint; smoother::Cint; restriction::Cint
-    device::Cint; use_graph::Cint; smem_levels::Cint
+    device::Cint; use_graph::Cint; smem_levels::Cint; fuse_sweeps::Cint
 end
 
 mutable struct MGHandle
@@ -133,7 +133,7 @@ end
 """preallocate_buffers(nx, ny) (multigrid.jl:25-38): level table, work arrays and the captured V-cycle graph."""
 function preallocate_buffers(nx, ny; opt=MGOpt())
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    cfg = MGConfig(nx, ny, opt.coarse_solve_size, Int(opt.coarse_solver), 0, 0, CUDA.deviceid(CUDA.device()), 1, 1)
+    cfg = MGConfig(nx, ny, opt.coarse_solve_size, Int(opt.coarse_solver), 0, 0, CUDA.deviceid(CUDA.device()), 1, 1, 1)
     check(ccall((:b2s_mg_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{MGConfig}), h, cfg))
     hd = MGHandle(h[], nx, ny)
     finalizer(x -> ccall((:b2s_mg_destroy, lib), Cint, (Ptr{Cvoid},), x.ptr), hd)

@@ -30,7 +30,8 @@ class MGOpt:
     """multigrid.jl:16-22 (+ the variant-B switches of this library: smoother, restriction)."""
 
     def __init__(self, coarse_solve_size=5, coarse_solver=jacobi, execution_policy=parallel_shmem,
-                 smoother=capi.SMOOTH_JACOBI, restriction=capi.RESTRICT_INJECT, use_graph=True, smem_levels=True):
+                 smoother=capi.SMOOTH_JACOBI, restriction=capi.RESTRICT_INJECT, use_graph=True, smem_levels=True,
+                 fuse_sweeps=True):
         self.coarse_solve_size = coarse_solve_size
         self.coarse_solver = coarse_solver
         self.execution_policy = execution_policy
@@ -38,6 +39,7 @@ class MGOpt:
         self.restriction = restriction
         self.use_graph = use_graph
         self.smem_levels = smem_levels
+        self.fuse_sweeps = fuse_sweeps
 
 
 def _torch():
@@ -83,7 +85,7 @@ class MGHandle:
         self._L = capi.lib()
         self.nx, self.ny, self.opt, self.device = nx, ny, opt, device
         cfg = capi.MGConfig(nx, ny, opt.coarse_solve_size, opt.coarse_solver, opt.smoother, opt.restriction, device,
-                            int(bool(opt.use_graph)), int(bool(opt.smem_levels)))
+                            int(bool(opt.use_graph)), int(bool(opt.smem_levels)), int(bool(opt.fuse_sweeps)))
         self._h = C.c_void_p()
         if opt.execution_policy == serial:
             raise capi.B2SError(capi.ERR_NOT_IMPLEMENTED, "execution policy serial is a CPU-only debug path")
@@ -283,7 +285,8 @@ class NavierStokes2D:
         p = capi.NS2DParams(opt.k, opt.Ra, opt.Pr, opt.nx, opt.ny, opt.ttot, opt.beta, opt.niters, opt.tol, opt.a_dif,
                             opt.a_adv)
         cfg = capi.MGConfig(opt.nx, opt.ny, mgopt.coarse_solve_size, mgopt.coarse_solver, mgopt.smoother,
-                            mgopt.restriction, device, int(bool(mgopt.use_graph)), int(bool(mgopt.smem_levels)))
+                            mgopt.restriction, device, int(bool(mgopt.use_graph)), int(bool(mgopt.smem_levels)),
+                            int(bool(mgopt.fuse_sweeps)))
         self.shape = (opt.nx, opt.ny)
         self._h = C.c_void_p()
         capi.check(self._L.b2s_ns2d_create(C.byref(self._h), C.byref(p), C.byref(cfg)))

@@ -101,8 +101,10 @@ def test_l0_bcs_reductions_axpy_rbgs(p2, oracle):
 
 
 CONFIGS = [
-    dict(),                                             # defaults: graph + collapsed coarse levels, cs=5, Jacobi
+    dict(),                                             # defaults: graph + collapsed coarse + fused tiles, cs=5, Jacobi
+    dict(fuse_sweeps=False),                            # one kernel per sweep / transfer operator
     dict(use_graph=False),
+    dict(use_graph=False, fuse_sweeps=False, smem_levels=False),
     dict(smem_levels=False),
     dict(coarse_solve_size=9),
     dict(coarse_solver=1),                              # CG coarse solver
@@ -274,13 +276,13 @@ def test_full_size_properties(p2):
         b = rnd((n, n), 1)
         db = p2.to_device(b)
         outs = []
-        for use_graph in (True, False):
+        for use_graph, fuse in ((True, True), (False, True), (True, False)):
             x = p2.zeros(n, n)
-            r, nc = p2.MGsolve_2DPoisson(x, db, 1.0 / (n - 1), 0.0, 1e-6, 100, False, opt=p2.MGOpt(use_graph=use_graph),
-                                         return_cycles=True)
+            r, nc = p2.MGsolve_2DPoisson(x, db, 1.0 / (n - 1), 0.0, 1e-6, 100, False,
+                                         opt=p2.MGOpt(use_graph=use_graph, fuse_sweeps=fuse), return_cycles=True)
             assert nc == 7 and r < 1e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
             outs.append(p2.to_host(x))
-        assert np.array_equal(outs[0], outs[1])
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
         # the discrete equation holds to the solver tolerance on the interior
         x = outs[0]
         lap = (x[2:, 1:-1] + x[:-2, 1:-1] + x[1:-1, 2:] + x[1:-1, :-2] - 4 * x[1:-1, 1:-1]) * (n - 1) ** 2

@@ -29,7 +29,7 @@ def test_no_cpu_fallback(b2s):
     with pytest.raises(capi.B2SError) as e:
         part1.Diffusion3D(32, 32, 32)
     assert e.value.code == capi.ERR_NO_DEVICE
-    cfg = capi.MGConfig(129, 129, 5, 0, 0, 0, 0, 1, 1)
+    cfg = capi.MGConfig(129, 129, 5, 0, 0, 0, 0, 1, 1, 1)
     h = C.c_void_p()
     assert capi.lib().b2s_mg_create(C.byref(h), C.byref(cfg)) == capi.ERR_NO_DEVICE
 
