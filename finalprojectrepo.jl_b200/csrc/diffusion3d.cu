@@ -94,6 +94,7 @@ static int pick_zchunk(int nxy_tiles, int nz, int max_blocks)
     if (zc <= 0) {
         const int want_blocks = 148 * 8;
         int chunks = (want_blocks + nxy_tiles - 1) / nxy_tiles;
+        chunks = std::max(chunks, (interior + 32) / 64);  // measured on B200: ~64 planes per chunk is the sweet spot
         chunks = std::max(1, std::min(chunks, interior / 16 > 0 ? interior / 16 : 1));
         zc = (interior + chunks - 1) / chunks;
     }

@@ -184,13 +184,12 @@ __global__ void __launch_bounds__((TX / 2) * TY)
     step_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapHt, const StepParams p)
 {
     using C = TmaCfg<TX, TY>;
-    extern __shared__ unsigned char smem_dyn[];
+    extern __shared__ __align__(128) unsigned char smem_dyn[];  // TMA destinations need 128-byte alignment
     __shared__ double red[32];
     if (p.state != nullptr && p.state->done) return;
 
-    // 128-byte aligned carve-up of the dynamic shared memory
-    unsigned char *base = (unsigned char *)(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
-    double *sA = (double *)base;
+    // carve-up of the dynamic shared memory (kept in the shared state space: plain LDS/STS, no generic loads)
+    double *sA = reinterpret_cast<double *>(smem_dyn);
     double *sH = sA + (size_t)S * C::A_STRIDE;
     uint64_t *full = (uint64_t *)(sH + (size_t)S * C::H_STRIDE);
 

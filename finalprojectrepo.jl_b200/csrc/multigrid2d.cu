@@ -52,9 +52,47 @@ struct b2s_mg {
     long long kernel_launches = 0;
     long long launches_per_cycle = 0;
     double last_ms = 0.0;
+    int tile_choice = 0;
 };
 
 namespace {
+
+// tile shapes of the temporally blocked kernels (B2S_MG_TILE selects; 0 is the tuned default)
+template <int TW, int TH>
+void launch_tile_t(bool up, const TileArgs &t, cudaStream_t st)
+{
+    dim3 g((t.nx + TW - 1) / TW, (t.ny + TH - 1) / TH, 1);
+    if (up) mg_up_kernel<TW, TH><<<g, kTileThreads, TileCfg<TW, TH>::kSmemBytes, st>>>(t);
+    else mg_down_kernel<TW, TH><<<g, kTileThreads, TileCfg<TW, TH>::kSmemBytes, st>>>(t);
+}
+void launch_tile(int choice, bool up, const TileArgs &t, cudaStream_t st)
+{
+    switch (choice) {
+    default:
+    case 0: launch_tile_t<64, 16>(up, t, st); break;
+    case 1: launch_tile_t<32, 32>(up, t, st); break;
+    case 2: launch_tile_t<64, 32>(up, t, st); break;
+    case 3: launch_tile_t<128, 16>(up, t, st); break;
+    }
+}
+template <int TW, int TH>
+cudaError_t tile_set_attr_t()
+{
+    cudaError_t e = cudaFuncSetAttribute(mg_down_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TileCfg<TW, TH>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mg_up_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<TW, TH>::kSmemBytes);
+}
+cudaError_t tile_set_attr(int choice)
+{
+    switch (choice) {
+    default:
+    case 0: return tile_set_attr_t<64, 16>();
+    case 1: return tile_set_attr_t<32, 32>();
+    case 2: return tile_set_attr_t<64, 32>();
+    case 3: return tile_set_attr_t<128, 16>();
+    }
+}
 
 // Enqueues one V-cycle (multigrid.jl:91-170) on `st`; counts kernel launches.
 int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
@@ -110,12 +148,12 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         t.partials = h->partials; t.ticket = h->ticket; t.sumsq_out = h->sumsq_dev;
         return t;
     };
-    auto tile_grid = [&](int l) { return dim3((h->nx[l] + kTW - 1) / kTW, (h->ny[l] + kTH - 1) / kTH, 1); };
+    const int tile_choice = h->tile_choice;
     // downward leg on the global-memory levels
     for (int l = 0; l < fs && fused; ++l) {
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
-        mg_down_kernel<<<tile_grid(l), kTileThreads, kTileSmemBytes, st>>>(t);
+        launch_tile(tile_choice, false, t, st);
         ++n;
     }
     for (int l = 0; l < fs && !fused; ++l) {
@@ -146,7 +184,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        mg_up_kernel<<<tile_grid(l), kTileThreads, kTileSmemBytes, st>>>(t);
+        launch_tile(tile_choice, true, t, st);
         ++n;
     }
     for (int l = fs - 1; l >= 0 && !fused; --l) {
@@ -347,8 +385,12 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
     MG_CUDA(cudaMalloc(&h->ticket, 64));
     MG_CUDA(cudaMemset(h->ticket, 0, 64));
     MG_CUDA(cudaFuncSetAttribute(mg_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemLimit + 1024));
-    MG_CUDA(cudaFuncSetAttribute(mg_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-    MG_CUDA(cudaFuncSetAttribute(mg_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+    {
+        const char *e = getenv("B2S_MG_TILE");
+        h->tile_choice = (e && *e) ? atoi(e) : 0;
+        if (h->tile_choice < 0 || h->tile_choice > 3) h->tile_choice = 0;
+        MG_CUDA(tile_set_attr(h->tile_choice));
+    }
 #undef MG_CUDA
     *out = h;
     return B2S_OK;

@@ -336,10 +336,15 @@ __global__ void __launch_bounds__(kMGBX) mg_prolong_smooth_kernel(const ProlongS
 // Every point value is produced by exactly the arithmetic of the unfused kernels (halo points are recomputed
 // redundantly by neighbouring blocks), so results are bit-identical to them.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kTW = 64, kTH = 32, kTileThreads = 256;
-constexpr int kTP = kTW + 8;  // shared-memory row pitch (tile + 2*3 halo, padded)
-constexpr int kTRows = kTH + 6;
-constexpr size_t kTileSmemBytes = (size_t)3 * kTP * kTRows * sizeof(double);
+constexpr int kTileThreads = 256;
+template <int TW, int TH>
+struct TileCfg {
+    static constexpr int kTW = TW, kTH = TH;
+    static constexpr int kTP = TW + 8;  // shared-memory row pitch (tile + 2*3 halo, padded)
+    static constexpr int kTRows = TH + 6;
+    static constexpr int kCW = TW / 2 + 3, kCH = TH / 2 + 3;  // coarse window staged by the upward kernel
+    static constexpr size_t kSmemBytes = ((size_t)3 * kTP * kTRows + (size_t)kCW * kCH) * sizeof(double);
+};
 
 struct TileArgs {
     const MGCall *cp;
@@ -356,18 +361,37 @@ struct TileArgs {
     double *sumsq_out;
 };
 
-// one Jacobi sweep inside shared memory over the window [x0,x1) x [y0,y1) of global coordinates (clipped to the domain)
+// 8-byte asynchronous global->shared copy (LDGSTS); pred == false zero-fills the destination without reading.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src, bool pred)
+{
+    const int src_bytes = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// one Jacobi sweep inside shared memory over a window of global coordinates. CHECKED = false: the whole window is
+// known to lie in the interior of the domain (no per-point tests).
+template <int kTP, bool CHECKED>
 __device__ __forceinline__ void tile_sweep(const double *__restrict__ src, const double *__restrict__ F, double *__restrict__ dst,
                                            int gx0, int gy0, int wx0, int wy0, int W, int H, int nx, int ny, const Coef &k)
 {
     // (gx0, gy0): global coordinates of shared-memory element (0,0); window origin (wx0, wy0), size W x H
+    const int s0 = (wy0 - gy0) * kTP + (wx0 - gx0);
     for (int idx = threadIdx.x; idx < W * H; idx += kTileThreads) {
         const int r = idx / W, c = idx - r * W;
-        const int i = wx0 + c, j = wy0 + r;
-        if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
-        const int s = (j - gy0) * kTP + (i - gx0);
+        const int s = s0 + r * kTP + c;
         double v = src[s];
-        if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
+        bool upd = true;
+        if (CHECKED) {
+            const int i = wx0 + c, j = wy0 + r;
+            if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
+            upd = i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
+        }
+        if (upd) {
             const double res = ((src[s + 1] + src[s - 1] + src[s + kTP] + src[s - kTP] - k.C * v) * k._h2 - F[s]);
             v = v + k.w * res;
         }
@@ -375,9 +399,13 @@ __device__ __forceinline__ void tile_sweep(const double *__restrict__ src, const
     }
 }
 
+template <int TW, int TH>
 __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
 {
-    extern __shared__ double tsm[];
+    using Cf = TileCfg<TW, TH>;
+    constexpr int kTW = Cf::kTW, kTH = Cf::kTH, kTP = Cf::kTP, kTRows = Cf::kTRows, kCW = Cf::kCW, kCH = Cf::kCH;
+    (void)kCW; (void)kCH; (void)kTRows;
+    extern __shared__ __align__(16) double tsm[];
     double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
     const MGCall *cp = a.cp;
     const double *u = a.u_in, *rhs = a.rhs;
@@ -387,19 +415,28 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     const int nx = a.nx, ny = a.ny;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int gx0 = X0 - 3, gy0 = Y0 - 3;
-    // stage u on tile+3 and rhs on tile+2
+    // stage u on tile+3 and rhs on tile+2 (asynchronous copies: all loads of the block are in flight at once)
     for (int idx = threadIdx.x; idx < (kTW + 6) * kTRows; idx += kTileThreads) {
         const int r = idx / (kTW + 6), c = idx - r * (kTW + 6);
         const int i = gx0 + c, j = gy0 + r;
         const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
-        const size_t p = (size_t)i + (size_t)nx * j;
-        A[r * kTP + c] = in ? u[p] : 0.0;
-        F[r * kTP + c] = (in && c >= 1 && c < kTW + 5 && r >= 1 && r < kTRows - 1) ? rhs[p] : 0.0;
+        const size_t p = in ? (size_t)i + (size_t)nx * j : 0;
+        cp_async8(A + r * kTP + c, u + p, in);
+        cp_async8(F + r * kTP + c, rhs + p, in && c >= 1 && c < kTW + 5 && r >= 1 && r < kTRows - 1);
     }
+    cp_async_wait_all();
     __syncthreads();
-    tile_sweep(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k);
-    __syncthreads();
-    tile_sweep(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    // block-uniform: does the widest stencil window stay strictly inside the domain?
+    const bool inner = X0 - 2 >= 1 && Y0 - 2 >= 1 && X0 + kTW + 1 <= nx - 2 && Y0 + kTH + 1 <= ny - 2;
+    if (inner) {
+        tile_sweep<kTP, false>(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k);
+        __syncthreads();
+        tile_sweep<kTP, false>(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    } else {
+        tile_sweep<kTP, true>(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k);
+        __syncthreads();
+        tile_sweep<kTP, true>(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    }
     __syncthreads();
     // smoothed u out
     for (int idx = threadIdx.x; idx < kTW * kTH; idx += kTileThreads) {
@@ -409,7 +446,6 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     }
     // coarse rhs = injected residual of the smoothed u (+ Neumann copies), coarse unknown = 0
     const int nxc = a.nxc, nyc = a.nyc;
-    const Coef kr = make_coef(level_h(cp, a.level), cp->c, 1.0);
     for (int idx = threadIdx.x; idx < (kTW / 2) * (kTH / 2); idx += kTileThreads) {
         const int r = idx / (kTW / 2), c = idx - r * (kTW / 2);
         const int I = X0 / 2 + c, J = Y0 / 2 + r;
@@ -419,7 +455,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
         const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
         if (interior) {
             const int s = (2 * r + 3) * kTP + 2 * c + 3;
-            const double v = ((A[s + 1] + A[s - 1] + A[s + kTP] + A[s - kTP] - kr.C * A[s]) * kr._h2 - F[s]);
+            const double v = ((A[s + 1] + A[s - 1] + A[s + kTP] + A[s - kTP] - k.C * A[s]) * k._h2 - F[s]);
             a.rc[pc] = v;
             if (apply_bcs) {  // coarse[0,:] = coarse[1,:] ; coarse[nxc-1,:] = coarse[nxc-2,:]
                 if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
@@ -431,11 +467,33 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     }
 }
 
+// bilinear prolongation from the staged coarse window (boundary-ring entries were staged as 0)
+template <int kCW>
+__device__ __forceinline__ double prolong_from_window(const double *__restrict__ Cw, int cx0, int cy0, int nx, int i, int j,
+                                                      int apply_bcs)
+{
+    if (apply_bcs) {
+        if (i == 0) i = 1;
+        else if (i == nx - 1) i = nx - 2;
+    }
+    const int I = (i >> 1) - cx0, J = (j >> 1) - cy0;
+    const double *q = Cw + J * kCW + I;
+    const bool io = i & 1, jo = j & 1;
+    if (!io && !jo) return q[0];
+    if (io && !jo) return 0.5 * q[0] + 0.5 * q[1];
+    if (!io && jo) return 0.5 * q[0] + 0.5 * q[kCW];
+    return ((0.25 * q[0] + 0.25 * q[1]) + 0.25 * q[kCW]) + 0.25 * q[kCW + 1];
+}
+
+template <int TW, int TH>
 __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
 {
-    extern __shared__ double tsm[];
+    using Cf = TileCfg<TW, TH>;
+    constexpr int kTW = Cf::kTW, kTH = Cf::kTH, kTP = Cf::kTP, kTRows = Cf::kTRows, kCW = Cf::kCW, kCH = Cf::kCH;
+    (void)kCW; (void)kCH; (void)kTRows;
+    extern __shared__ __align__(16) double tsm[];
     __shared__ double red[32];
-    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
+    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows, *Cw = tsm + 3 * kTP * kTRows;
     const MGCall *cp = a.cp;
     const double *rhs = a.rhs;
     double *out = a.u_out;
@@ -445,18 +503,37 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int gx0 = X0 - 3, gy0 = Y0 - 3;
-    // corrected u = u_s - P(ec) on tile+2, rhs on tile+1
+    const int cx0 = X0 / 2 - 1, cy0 = Y0 / 2 - 1;
+    // stage the smoothed u on tile+2, rhs on tile+1 and the coarse correction window
     for (int idx = threadIdx.x; idx < (kTW + 4) * (kTH + 4); idx += kTileThreads) {
         const int r = idx / (kTW + 4), c = idx - r * (kTW + 4);
         const int i = X0 - 2 + c, j = Y0 - 2 + r;
         const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
-        const size_t p = (size_t)i + (size_t)nx * j;
+        const size_t p = in ? (size_t)i + (size_t)nx * j : 0;
         const int s = (r + 1) * kTP + c + 1;
-        A[s] = in ? a.u_in[p] - prolong_value_bc(a.ec, nxc, nyc, nx, i, j, apply_bcs) : 0.0;
-        F[s] = (in && c >= 1 && c < kTW + 3 && r >= 1 && r < kTH + 3) ? rhs[p] : 0.0;
+        cp_async8(A + s, a.u_in + p, in);
+        cp_async8(F + s, rhs + p, in && c >= 1 && c < kTW + 3 && r >= 1 && r < kTH + 3);
+    }
+    for (int idx = threadIdx.x; idx < kCW * kCH; idx += kTileThreads) {
+        const int r = idx / kCW, c = idx - r * kCW;
+        const int I = cx0 + c, J = cy0 + r;
+        const bool in = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;  // the boundary ring counts as 0
+        cp_async8(Cw + idx, a.ec + (in ? (size_t)I + (size_t)nxc * J : 0), in);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // u_f .= u_f - corr_f on tile+2
+    for (int idx = threadIdx.x; idx < (kTW + 4) * (kTH + 4); idx += kTileThreads) {
+        const int r = idx / (kTW + 4), c = idx - r * (kTW + 4);
+        const int i = X0 - 2 + c, j = Y0 - 2 + r;
+        if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
+        const int s = (r + 1) * kTP + c + 1;
+        A[s] = A[s] - prolong_from_window<kCW>(Cw, cx0, cy0, nx, i, j, apply_bcs);
     }
     __syncthreads();
-    tile_sweep(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    const bool inner = X0 - 1 >= 1 && Y0 - 1 >= 1 && X0 + kTW <= nx - 2 && Y0 + kTH <= ny - 2;
+    if (inner) tile_sweep<kTP, false>(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    else tile_sweep<kTP, true>(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
     __syncthreads();
     double acc = 0.0;
     for (int idx = threadIdx.x; idx < kTW * kTH; idx += kTileThreads) {
@@ -595,6 +672,21 @@ struct WarpGroup {
     __device__ __forceinline__ double sum(double v) const { return warp_sum(v); }
 };
 
+// (i, j) of a strided flat index, advanced without a division per point
+struct Idx2 {
+    int p, i, j, di, dj, nx, stride;
+    __device__ __forceinline__ Idx2(int rank, int stride_, int nx_) : p(rank), nx(nx_), stride(stride_)
+    {
+        j = rank / nx_; i = rank - j * nx_;
+        dj = stride_ / nx_; di = stride_ - dj * nx_;
+    }
+    __device__ __forceinline__ void next()
+    {
+        p += stride; i += di; j += dj;
+        if (i >= nx) { i -= nx; ++j; }
+    }
+};
+
 template <class G>
 __device__ __forceinline__ void sm_fill(const G &g, double *a, int n, double v)
 {
@@ -608,8 +700,8 @@ __device__ __forceinline__ double sm_jacobi(const G &g, const double *u, const d
 {
     double acc = 0.0;
     const int n = nx * ny;
-    for (int p = g.rank(); p < n; p += g.size()) {
-        const int i = p % nx, j = p / nx;
+    for (Idx2 q(g.rank(), g.size(), nx); q.p < n; q.next()) {
+        const int p = q.p, i = q.i, j = q.j;
         if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
             const double r = ((u[p + 1] + u[p - 1] + u[p + nx] + u[p - nx] - k.C * u[p]) * k._h2 - rhs[p]);
             acc += r * r;
@@ -634,8 +726,8 @@ __device__ __forceinline__ double sm_rbgs(const G &g, double *u, const double *r
     const int n = nx * ny;
     for (int colour = 0; colour < 2; ++colour) {
         double acc = 0.0;
-        for (int p = g.rank(); p < n; p += g.size()) {
-            const int i = p % nx, j = p / nx;
+        for (Idx2 q(g.rank(), g.size(), nx); q.p < n; q.next()) {
+            const int p = q.p, i = q.i, j = q.j;
             if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2 && ((i + j + colour) & 1) == 0) {
                 const double r = (u[p + 1] + u[p - 1] + u[p + nx] + u[p - nx] - C * u[p]) / h2 - rhs[p];
                 u[p] = u[p] + w * r;
@@ -780,9 +872,9 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
             sm_jacobi(bg, T[l], F[l], U[l], nx, ny, k, false);
         }
         const Coef kr = make_coef(h, c, 1.0);
-        for (int p = threadIdx.x; p < nxc * nyc; p += blockDim.x) {
-            int I = p % nxc;
-            const int J = p / nxc;
+        for (Idx2 q(threadIdx.x, blockDim.x, nxc); q.p < nxc * nyc; q.next()) {
+            const int p = q.p, J = q.j;
+            int I = q.i;
             if (apply_bcs) {
                 if (I == 0) I = 1;
                 else if (I == nxc - 1) I = nxc - 2;
@@ -812,10 +904,8 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
         const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
         const double h = level_h(cp, a.level0 + l);
         const Coef k = make_coef(h, c, 4.0 / 5.0);
-        for (int p = threadIdx.x; p < nx * ny; p += blockDim.x) {
-            const int i = p % nx, j = p / nx;
-            U[l][p] = U[l][p] - prolong_value_bc(U[l + 1], nxc, nyc, nx, i, j, apply_bcs);
-        }
+        for (Idx2 q(threadIdx.x, blockDim.x, nx); q.p < nx * ny; q.next())
+            U[l][q.p] = U[l][q.p] - prolong_value_bc(U[l + 1], nxc, nyc, nx, q.i, q.j, apply_bcs);
         __syncthreads();
         const bool top = (l == 0 && a.sumsq_out != nullptr);
         if (a.smoother == B2S_SMOOTH_RBGS) {
