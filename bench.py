@@ -166,9 +166,14 @@ def mg_bench(device, peak):
     except Exception as e:  # pragma: no cover
         return {"unavailable": f"{type(e).__name__}: {e}"}
     try:
-        return part2.bench_vcycle(device=device, hbm_peak_gbs=peak)
+        out = part2.bench_vcycle(device=device, hbm_peak_gbs=peak)
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {e}"}
+    try:
+        out["navier_stokes_2049"] = part2.bench_navier_stokes(device=device)
+    except Exception as e:  # pragma: no cover
+        out["navier_stokes_2049"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def main():

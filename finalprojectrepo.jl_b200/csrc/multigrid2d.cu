@@ -53,6 +53,8 @@ struct b2s_mg {
     long long launches_per_cycle = 0;
     double last_ms = 0.0;
     int tile_choice = 0;
+    int stream_ch = 0;
+    long long *prof_dev = nullptr;  // B2S_MG_PROF=1: phase stamps of the collapsed coarse kernel
 };
 
 namespace {
@@ -150,10 +152,30 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     };
     const int tile_choice = h->tile_choice;
     // downward leg on the global-memory levels
+    const bool streaming = c.fuse_sweeps != 2;
+    auto stream_rows = [&](int l) {
+        // rows per chunk (even, >= 16, <= ~256): the grid should fill whole waves of 148 SMs x 6 resident blocks
+        const int bx = (h->nx[l] + kSW - 1) / kSW, ny = h->ny[l], slots = 148 * 6;
+        int ch = 16;
+        for (int w = 1; w <= 64; ++w) {
+            const int chunks = std::max(1, (w * slots) / bx);
+            ch = (ny + chunks - 1) / chunks;
+            if (ch <= 256) break;
+        }
+        if (h->stream_ch > 0) ch = h->stream_ch;
+        ch = std::max(16, (ch + 1) & ~1);
+        return ch;
+    };
+    auto stream_grid = [&](int l, int ch) { return dim3((h->nx[l] + kSW - 1) / kSW, (h->ny[l] + ch - 1) / ch, 1); };
     for (int l = 0; l < fs && fused; ++l) {
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
-        launch_tile(tile_choice, false, t, st);
+        if (streaming) {
+            const int ch = stream_rows(l);
+            mg_down_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
+        } else {
+            launch_tile(tile_choice, false, t, st);
+        }
         ++n;
     }
     for (int l = 0; l < fs && !fused; ++l) {
@@ -177,6 +199,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         a.coarse_solve_size = c.coarse_solve_size; a.coarse_solver = c.coarse_solver;
         a.smoother = c.smoother; a.restriction = c.restriction;
         a.sumsq_out = fs == 0 ? h->sumsq_dev : nullptr;
+        a.prof = h->prof_dev;
         mg_coarse_kernel<<<1, 1024, h->coarse_smem, st>>>(a);
         ++n;
     }
@@ -184,7 +207,12 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        launch_tile(tile_choice, true, t, st);
+        if (streaming) {
+            const int ch = stream_rows(l);
+            mg_up_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
+        } else {
+            launch_tile(tile_choice, true, t, st);
+        }
         ++n;
     }
     for (int l = fs - 1; l >= 0 && !fused; --l) {
@@ -270,6 +298,7 @@ int mg_destroy_impl(b2s_mg *h)
     if (h->sweeps_dev) cudaFree(h->sweeps_dev);
     if (h->partials) cudaFree(h->partials);
     if (h->ticket) cudaFree(h->ticket);
+    if (h->prof_dev) cudaFree(h->prof_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -390,6 +419,13 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         h->tile_choice = (e && *e) ? atoi(e) : 0;
         if (h->tile_choice < 0 || h->tile_choice > 3) h->tile_choice = 0;
         MG_CUDA(tile_set_attr(h->tile_choice));
+        const char *e2 = getenv("B2S_MG_CH");
+        h->stream_ch = (e2 && *e2) ? atoi(e2) : 0;
+        const char *e3 = getenv("B2S_MG_PROF");
+        if (e3 && *e3 == '1') {
+            MG_CUDA(cudaMalloc(&h->prof_dev, 64 * sizeof(long long)));
+            MG_CUDA(cudaMemset(h->prof_dev, 0, 64 * sizeof(long long)));
+        }
     }
 #undef MG_CUDA
     *out = h;
@@ -451,6 +487,13 @@ int b2s_mg_vcycle(b2s_mg *h, double *u, const double *rhs, double hgrid, double 
     B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     B2S_CUDA(cudaStreamSynchronize(h->stream));
     if (res_rms) *res_rms = sqrt(h->sumsq_pin[0] / ((double)h->nx[0] * h->ny[0]));
+    if (h->prof_dev) {
+        long long p[64];
+        B2S_CUDA(cudaMemcpy(p, h->prof_dev, sizeof(p), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[b2s mg_coarse_kernel phases, SM cycles since entry]");
+        for (long long i = 1; i < p[0] && i < 60; ++i) fprintf(stderr, " %lld", p[1 + i] - p[1]);
+        fprintf(stderr, "\n");
+    }
     return B2S_OK;
 }
 

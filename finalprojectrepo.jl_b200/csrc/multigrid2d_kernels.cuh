@@ -558,6 +558,237 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming (y-marching) versions of the two fused level kernels. A block owns a strip of kSW columns (+3 halo columns
+// per side, one thread per column) and marches over a chunk of rows; rows of u and rhs arrive through a cp.async ring
+// kSD rows ahead of use, every pipeline stage (sweep 1, sweep 2, residual/output) trails the previous one by one row,
+// a thread keeps the y neighbours of its own column in registers and reads only the x neighbours from shared memory.
+// One __syncthreads per row, no redundant rows except 3 (2) warm-up rows per chunk, ~3x fewer instructions per point
+// than the tile kernels; same arithmetic per point, hence bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSNT = 128;         // threads per block = strip columns including the halo
+constexpr int kSW = kSNT - 6;     // output columns per strip (even)
+constexpr int kSD = 6;            // prefetch depth in rows
+constexpr int kSRing = 12;        // ring rows for the streamed inputs (> kSD + 2, a multiple of 4; = unroll factor)
+constexpr int kSCRing = kSRing / 2;  // coarse-row ring of the upward kernel
+constexpr int kSP = kSNT + 2;     // ring row pitch: one pad element on each side
+constexpr int kSCW = kSW / 2 + 5; // coarse window width of the upward kernel
+constexpr int kSCP = kSCW + 1;
+
+// Ring slots are relative to the first streamed row of the block, and the row loop is unrolled by the ring size, so
+// every shared-memory index below is a compile-time constant and the register queues rotate by renaming.
+__global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, int ch)
+{
+    __shared__ double U0[kSRing][kSP], Fr[kSRing][kSP], S1[4][kSP], S2[4][kSP];
+    const MGCall *cp = a.cp;
+    const double *u = a.u_in, *rhs = a.rhs;
+    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int t = threadIdx.x, c = t + 1;
+    const int X0 = blockIdx.x * kSW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);
+    const int x = X0 - 3 + t;
+    const bool dx = x >= 0 && x < nx, ix = x >= 1 && x <= nx - 2;
+    const bool outcol = t >= 3 && t <= kSNT - 4 && dx;
+    if (t == 0) {  // pads are read by the (unused) edge columns only; keep them finite
+        for (int r = 0; r < kSRing; ++r) { U0[r][0] = 0.0; U0[r][kSP - 1] = 0.0; }
+        for (int r = 0; r < 4; ++r) { S1[r][0] = 0.0; S1[r][kSP - 1] = 0.0; S2[r][0] = 0.0; S2[r][kSP - 1] = 0.0; }
+    }
+    const int s_begin = Y0 - 3, s_end = Y1 + 2;
+    const double *gu = u + (dx ? x : 0), *gf = rhs + (dx ? x : 0);
+#pragma unroll
+    for (int j = 0; j < kSD; ++j) {  // prologue: rows s_begin .. s_begin+kSD-1 -> slots 0 .. kSD-1
+        const int r = s_begin + j;
+        const bool in = dx && r >= 0 && r < ny;
+        const size_t off = in ? (size_t)nx * r : 0;
+        cp_async8(&U0[j][c], gu + off, in);
+        cp_async8(&Fr[j][c], gf + off, in);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    double u_a = 0.0, u_b = 0.0, u_c = 0.0;  // U0 rows s-2, s-1, s of this column
+    double p_a = 0.0, p_b = 0.0;             // S1 rows s-3, s-2
+    double q_a = 0.0, q_b = 0.0;             // S2 rows s-4, s-3
+    double f_a = 0.0, f_b = 0.0, f_c = 0.0, f_d = 0.0;  // rhs rows s-3 .. s
+    for (int s0 = s_begin; s0 <= s_end; s0 += kSRing) {
+#pragma unroll
+        for (int j = 0; j < kSRing; ++j) {
+            const int s = s0 + j;
+            {
+                const int r = s + kSD;
+                const bool in = dx && r >= 0 && r < ny && r <= s_end;
+                const size_t off = in ? (size_t)nx * r : 0;
+                cp_async8(&U0[(j + kSD) % kSRing][c], gu + off, in);
+                cp_async8(&Fr[(j + kSD) % kSRing][c], gf + off, in);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group %0;" ::"n"(kSD) : "memory");
+            __syncthreads();
+            u_a = u_b; u_b = u_c; u_c = U0[j][c];
+            f_a = f_b; f_b = f_c; f_c = f_d; f_d = Fr[j][c];
+            // stage A: first sweep at row s-1
+            const int ya = s - 1;
+            double p_c = u_b;
+            if (ix && ya >= 1 && ya <= ny - 2) {
+                const double *row = U0[(j + kSRing - 1) % kSRing];
+                const double res = ((row[c + 1] + row[c - 1] + u_c + u_a - k.C * u_b) * k._h2 - f_c);
+                p_c = u_b + k.w * res;
+            }
+            S1[(j + 3) & 3][c] = p_c;
+            // stage B: second sweep at row s-2 (x neighbours of S1[s-2] were published one step ago)
+            const int yb = s - 2;
+            double q_c = p_b;
+            if (ix && yb >= 1 && yb <= ny - 2) {
+                const double *row = S1[(j + 2) & 3];
+                const double res = ((row[c + 1] + row[c - 1] + p_c + p_a - k.C * p_b) * k._h2 - f_b);
+                q_c = p_b + k.w * res;
+            }
+            S2[(j + 2) & 3][c] = q_c;
+            // stage C: output row s-3: smoothed u, injected residual -> coarse rhs, coarse unknown = 0
+            const int yc = s - 3;
+            if (yc >= Y0 && yc < Y1 && outcol) {
+                a.u_out[(size_t)x + (size_t)nx * yc] = q_b;
+                if (((x | yc) & 1) == 0) {
+                    const int I = x >> 1, J = yc >> 1;
+                    const size_t pc = (size_t)I + (size_t)nxc * J;
+                    a.ec[pc] = 0.0;
+                    const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
+                    if (interior) {
+                        const double *row = S2[(j + 1) & 3];
+                        const double v = ((row[c + 1] + row[c - 1] + q_c + q_a - k.C * q_b) * k._h2 - f_a);
+                        a.rc[pc] = v;
+                        if (apply_bcs) {
+                            if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                            if (I == nxc - 2) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+                        }
+                    } else if (!(apply_bcs && (I == 0 || I == nxc - 1) && J >= 1 && J <= nyc - 2)) {
+                        a.rc[pc] = 0.0;
+                    }
+                }
+            }
+            p_a = p_b; p_b = p_c;
+            q_a = q_b; q_b = q_c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, int ch)
+{
+    __shared__ double Us[kSRing][kSP], Fr[kSRing][kSP], C0[4][kSP], T1[4][kSP], Ec[kSCRing][kSCP];
+    __shared__ double red[32];
+    const MGCall *cp = a.cp;
+    const double *rhs = a.rhs;
+    double *out = a.u_out;
+    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int t = threadIdx.x, c = t + 1;
+    const int X0 = blockIdx.x * kSW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);  // ch is even
+    const int x = X0 - 3 + t;
+    const bool dx = x >= 0 && x < nx, ix = x >= 1 && x <= nx - 2;
+    const bool outcol = t >= 3 && t <= kSNT - 4 && dx;
+    const int cx0 = X0 / 2 - 2;
+    if (t == 0) {
+        for (int r = 0; r < 4; ++r) { C0[r][0] = 0.0; C0[r][kSP - 1] = 0.0; T1[r][0] = 0.0; T1[r][kSP - 1] = 0.0; }
+    }
+    // prolongation source column(s) of this thread (Neumann: fine[0,:] = fine[1,:], fine[nx-1,:] = fine[nx-2,:])
+    int xs = x;
+    if (apply_bcs) {
+        if (x == 0) xs = 1;
+        else if (x == nx - 1) xs = nx - 2;
+    }
+    const int Il = (xs >> 1) - cx0;  // local coarse column
+    const bool xodd = xs & 1;
+    const int s_begin = Y0 - 2, s_end = Y1 + 1;  // s_begin is even: row parity == slot parity
+    const int K0 = s_begin >> 1;                  // coarse row held by slot 0 of the coarse ring
+    const double *gu = a.u_in + (dx ? x : 0), *gf = rhs + (dx ? x : 0);
+    const int Ic = cx0 + t;
+    const bool cin = t < kSCW && Ic >= 1 && Ic <= nxc - 2;
+    const double *gc = a.ec + (cin ? Ic : 0);
+    // coarse row K = K0 + m goes to slot m % kSCRing (the boundary ring of the coarse grid counts as 0)
+    auto issue_coarse = [&](int m, int slot) {
+        if (t < kSCW) {
+            const int K = K0 + m;
+            const bool in = cin && K >= 1 && K <= nyc - 2;
+            cp_async8(&Ec[slot][t], gc + (in ? (size_t)nxc * K : 0), in);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < kSD; ++j) {
+        const int r = s_begin + j;
+        const bool in = dx && r >= 0 && r < ny;
+        const size_t off = in ? (size_t)nx * r : 0;
+        cp_async8(&Us[j][c], gu + off, in);
+        cp_async8(&Fr[j][c], gf + off, in);
+        if (j == 0) issue_coarse(0, 0);
+        if (j & 1) issue_coarse((j + 1) >> 1, ((j + 1) >> 1) % kSCRing);  // coarse row K is first needed by fine row 2K-1
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    double c_a = 0.0, c_b = 0.0;  // corrected u rows s-2, s-1
+    double t_a = 0.0, t_b = 0.0;  // first-sweep rows s-3, s-2
+    double f_a = 0.0, f_b = 0.0, f_c = 0.0;  // rhs rows s-2 .. s
+    double acc = 0.0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kSRing) {
+        const int m0 = (s0 - s_begin) >> 1;
+#pragma unroll
+        for (int j = 0; j < kSRing; ++j) {
+            const int s = s0 + j;
+            {
+                const int r = s + kSD;
+                const bool in = dx && r >= 0 && r < ny && r <= s_end;
+                const size_t off = in ? (size_t)nx * r : 0;
+                cp_async8(&Us[(j + kSD) % kSRing][c], gu + off, in);
+                cp_async8(&Fr[(j + kSD) % kSRing][c], gf + off, in);
+                if ((j + kSD) & 1) issue_coarse(m0 + ((j + kSD + 1) >> 1), ((j + kSD + 1) >> 1) % kSCRing);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group %0;" ::"n"(kSD) : "memory");
+            __syncthreads();
+            f_a = f_b; f_b = f_c; f_c = Fr[j][c];
+            // stage A: corrected u at row s:  u_s - P(ec)
+            double e;
+            {
+                const double *r0 = Ec[(j >> 1) % kSCRing] + Il, *r1 = Ec[((j >> 1) + 1) % kSCRing] + Il;
+                if (!(j & 1)) e = xodd ? 0.5 * r0[0] + 0.5 * r0[1] : r0[0];
+                else e = xodd ? ((0.25 * r0[0] + 0.25 * r0[1]) + 0.25 * r1[0]) + 0.25 * r1[1] : 0.5 * r0[0] + 0.5 * r1[0];
+            }
+            const double c_c = Us[j][c] - e;
+            C0[j & 3][c] = c_c;
+            // stage B: first post-sweep at row s-1
+            const int yb = s - 1;
+            double t_c = c_b;
+            if (ix && yb >= 1 && yb <= ny - 2) {
+                const double *row = C0[(j + 3) & 3];
+                const double res = ((row[c + 1] + row[c - 1] + c_c + c_a - k.C * c_b) * k._h2 - f_b);
+                t_c = c_b + k.w * res;
+            }
+            T1[(j + 3) & 3][c] = t_c;
+            // stage C: second post-sweep at row s-2 -> u, sum of its pre-update res^2
+            const int yc = s - 2;
+            if (yc >= Y0 && yc < Y1 && outcol) {
+                double v = t_b;
+                if (ix && yc >= 1 && yc <= ny - 2) {
+                    const double *row = T1[(j + 2) & 3];
+                    const double res = ((row[c + 1] + row[c - 1] + t_c + t_a - k.C * t_b) * k._h2 - f_a);
+                    acc += res * res;
+                    v = t_b + k.w * res;
+                }
+                out[(size_t)x + (size_t)nx * yc] = v;
+            }
+            c_a = c_b; c_b = c_c;
+            t_a = t_b; t_b = t_c;
+        }
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+    }
+}
+
 // apply_boundary_conditions!(T): Dirichlet T[:,0]=1, T[:,ny-1]=0, then Neumann T[0,:]=T[1,:], T[nx-1,:]=T[nx-2,:]
 // (part2_utils.jl:21-39). kind: 0 both, 1 Dirichlet only, 2 Neumann only.
 __global__ void mg_bc_kernel(const MGCall *cp, double *T, int nx, int ny, int kind)
@@ -647,7 +878,16 @@ struct CoarseArgs {
     int u_is_input;           // 1: start from the values in u_io (top-level coarsest solve); 0: start from zero
     int coarse_solve_size, coarse_solver, smoother, restriction;
     double *sumsq_out;        // nullable: sum res^2 of the last sweep when level0 == 0 has no finer level
+    long long *prof;          // nullable: clock64() stamps of the phases (B2S_MG_PROF=1), [0] = count
 };
+
+__device__ __forceinline__ void coarse_stamp(const CoarseArgs &a)
+{
+    if (a.prof != nullptr && threadIdx.x == 0) {
+        const long long n = a.prof[0];
+        if (n < 60) { a.prof[1 + n] = clock64(); a.prof[0] = n + 1; }
+    }
+}
 
 struct BlockGroup {
     double *red;
@@ -859,6 +1099,8 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
         __syncthreads();
     }
     double last_ss = 0.0;
+    if (a.prof != nullptr && threadIdx.x == 0) a.prof[0] = 0;
+    coarse_stamp(a);
     // ---- downward leg ---------------------------------------------------------------------------------------
     for (int l = 0; l + 1 < a.nlev; ++l) {
         const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
@@ -883,6 +1125,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
             U[l + 1][p] = 0.0;
         }
         __syncthreads();
+        coarse_stamp(a);
     }
     // ---- coarsest solve ---------------------------------------------------------------------------------------
     {
@@ -898,6 +1141,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
         } else {
             last_ss = sm_coarsest(bg, U[l], F[l], T[l], U[a.nlev], nx, ny, h, a, c, tol, cp->coarse_sweeps);
         }
+        coarse_stamp(a);
     }
     // ---- upward leg -------------------------------------------------------------------------------------------
     for (int l = a.nlev - 2; l >= 0; --l) {
@@ -915,12 +1159,15 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
             sm_jacobi(bg, U[l], F[l], T[l], nx, ny, k, false);
             last_ss = sm_jacobi(bg, T[l], F[l], U[l], nx, ny, k, top);
         }
+        coarse_stamp(a);
     }
     {
         const int n = a.nx[0] * a.ny[0];
         for (int p = threadIdx.x; p < n; p += blockDim.x) u_g[p] = U[0][p];
         if (a.sumsq_out != nullptr && threadIdx.x == 0) *a.sumsq_out = last_ss;
     }
+    __syncthreads();
+    coarse_stamp(a);
 }
 
 // Stand-alone CG for grids that fit into shared memory (test/krylov.jl shape: 66^2).

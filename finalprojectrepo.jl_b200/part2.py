@@ -85,7 +85,7 @@ class MGHandle:
         self._L = capi.lib()
         self.nx, self.ny, self.opt, self.device = nx, ny, opt, device
         cfg = capi.MGConfig(nx, ny, opt.coarse_solve_size, opt.coarse_solver, opt.smoother, opt.restriction, device,
-                            int(bool(opt.use_graph)), int(bool(opt.smem_levels)), int(bool(opt.fuse_sweeps)))
+                            int(bool(opt.use_graph)), int(bool(opt.smem_levels)), int(opt.fuse_sweeps))
         self._h = C.c_void_p()
         if opt.execution_policy == serial:
             raise capi.B2SError(capi.ERR_NOT_IMPLEMENTED, "execution policy serial is a CPU-only debug path")
@@ -286,7 +286,7 @@ class NavierStokes2D:
                             opt.a_adv)
         cfg = capi.MGConfig(opt.nx, opt.ny, mgopt.coarse_solve_size, mgopt.coarse_solver, mgopt.smoother,
                             mgopt.restriction, device, int(bool(mgopt.use_graph)), int(bool(mgopt.smem_levels)),
-                            int(bool(mgopt.fuse_sweeps)))
+                            int(mgopt.fuse_sweeps))
         self.shape = (opt.nx, opt.ny)
         self._h = C.c_void_p()
         capi.check(self._L.b2s_ns2d_create(C.byref(self._h), C.byref(p), C.byref(cfg)))
@@ -372,6 +372,12 @@ def mg_algorithmic_bytes(nx, ny, coarse_solve_size=5):
     return 132.0 * tot
 
 
+def mg_fused_min_bytes(nx, ny, coarse_solve_size=5):
+    """Compulsory traffic of the fused formulation (2 kernels per level): down reads u, f and writes u_s, rc/4, ec/4
+    (3.5 doubles per point), up reads u_s, f, ec/4 and writes u (3.25) = 54 B per point of every non-coarsest level."""
+    return mg_algorithmic_bytes(nx, ny, coarse_solve_size) / 132.0 * 54.0
+
+
 def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycles=50, seed=1):
     """Config #2 (multigrid_bench.jl shape): x = 0, b ~ U[0,1) on all entries, c = 0, tol 1e-6; DoF/s per V-cycle with
     fields resident on the device (CUDA events inside the library), plus the whole-solve time and cycle count."""
@@ -399,9 +405,40 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
         out["sizes"][str(n)] = {"dof_per_s": n * n / per, "ms_per_vcycle": per * 1e3, "vcycles_to_1e-6": nc,
                                 "solve_ms": solve_s * 1e3, "algorithmic_bytes_per_vcycle": ab,
                                 "achieved_gbs": ab / per / 1e9, "frac_of_hbm_peak": ab / per / 1e9 / hbm_peak_gbs,
+                                "fused_min_bytes_per_vcycle": mg_fused_min_bytes(n, n),
+                                "fused_achieved_gbs": mg_fused_min_bytes(n, n) / per / 1e9,
+                                "fused_frac_of_hbm_peak": mg_fused_min_bytes(n, n) / per / 1e9 / hbm_peak_gbs,
                                 "kernel_launches_per_vcycle": (l1 - l0) / ncycles}
         hd.close()
     return out
+
+
+def bench_navier_stokes(device=0, n=2049, steps=8, seed=1):
+    """Config #4: 2-D streamfunction-vorticity Navier-Stokes, semi-implicit (beta = 0.5, Pr = 0.1, tol 1e-7: the
+    published experiment's settings, part2_semi_implicit_vs_explicit_experiments.jl:38-44) on an n x n grid, W ~ U[0,1).
+    Times the steps from the 4th on (the reference starts its timer at step 3, part2.jl:182-184)."""
+    import warnings
+    torch = _torch()
+    opt = SimIn_t(nx=n, ny=n, beta=0.5, Pr=0.1, tol=1.0e-7, niters=50)
+    sim = NavierStokes2D(opt, MGOpt(), device)
+    sim.init_cosine("T")
+    sim.set_field("W", np.random.default_rng(seed).random((n, n)))
+    infos, t0 = [], None
+    for step in range(steps):
+        if step == 3:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        i = sim.step()
+        infos.append((i.dt, i.cycles_S, i.cycles_T, i.cycles_W))
+    torch.cuda.synchronize()
+    dt_wall = time.perf_counter() - t0
+    timed = infos[3:]
+    cyc = sum(a + b + c for _, a, b, c in timed)
+    sim.close()
+    return {"grid": [n, n], "beta": 0.5, "Pr": 0.1, "tol": 1e-7, "timed_steps": len(timed),
+            "ms_per_step": dt_wall / len(timed) * 1e3, "vcycles_per_step": cyc / len(timed),
+            "cycles_S_T_W": [list(x[1:]) for x in infos], "dof_per_s_per_vcycle": n * n * cyc / dt_wall,
+            "note": "whole time step incl. 3 MG solves, velocity/dt reduction, fused stencil + rhs kernel; host syncs per V-cycle"}
 
 
 def smoke_check(O):
