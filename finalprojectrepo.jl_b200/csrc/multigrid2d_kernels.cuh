@@ -1033,6 +1033,91 @@ __device__ __forceinline__ double sm_cg(const G &g, double *x_in, const double *
     return sm_sumsq(g, r, n);
 }
 
+// Exact threshold for the coarsest-level exit test: the reference stops when sqrt(ss/N) < T (multigrid.jl:150-156).
+// Correctly rounded division and sqrt are monotone, so {ss : sqrt(fl(ss/N)) < T} = [0, S*) for one double S*; it is
+// found once per solve (a few ulp steps around T*T*N) and the per-sweep test becomes `ss < S*` -- the same decisions
+// without a division and a square root on the critical path of every sweep.
+__device__ __forceinline__ double exit_threshold(double T, double N)
+{
+    if (!(T > 0.0)) return T == T ? 0.0 : T;  // T <= 0: never true (ss >= 0); NaN: comparisons stay false
+    double s = T * T * N;
+    if (!(s > 0.0) || s != s || s > 1.0e300) return s;  // underflow / overflow: keep the plain product
+    for (int i = 0; i < 64 && sqrt(s / N) < T; ++i) s = __longlong_as_double(__double_as_longlong(s) + 1);
+    for (int i = 0; i < 64; ++i) {
+        const double sp = __longlong_as_double(__double_as_longlong(s) - 1);
+        if (sqrt(sp / N) < T) break;
+        s = sp;
+    }
+    return s;
+}
+
+// One Jacobi sweep of a tiny grid inside one warp with the points of each lane precomputed (M points per lane).
+template <int M>
+struct WarpPoints {
+    int p[M];
+    bool valid[M], interior[M];
+    __device__ __forceinline__ WarpPoints(int nx, int ny)
+    {
+        const int lane = threadIdx.x & 31, n = nx * ny;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            p[m] = lane + 32 * m;
+            valid[m] = p[m] < n;
+            const int j = p[m] / nx, i = p[m] - j * nx;
+            interior[m] = valid[m] && i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
+        }
+    }
+    __device__ __forceinline__ double sweep(const double *src, const double *rhs, double *dst, int nx, const Coef &k) const
+    {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (interior[m]) {
+                const int q = p[m];
+                const double r = ((src[q + 1] + src[q - 1] + src[q + nx] + src[q - nx] - k.C * src[q]) * k._h2 - rhs[q]);
+                acc += r * r;
+                dst[q] = src[q] + k.w * r;
+            } else if (valid[m]) {
+                dst[p[m]] = src[p[m]];
+            }
+        }
+        return acc;
+    }
+};
+
+// Coarsest Jacobi solve in one warp, software-pipelined: sweep s+1 is computed speculatively (into the other
+// ping-pong buffer) while the residual norm of sweep s is still being reduced; if sweep s satisfied the exit test its
+// result is simply kept. Returns sum res^2 of the last counted sweep; the solution ends up in u.
+template <int M>
+__device__ __forceinline__ double warp_coarsest_jacobi(double *u, const double *rhs, double *tmp, int nx, int ny, const Coef &k,
+                                                       double sstar, int iters, int *sweeps_out)
+{
+    const WarpPoints<M> wp(nx, ny);
+    const int n = nx * ny;
+    double *cur = u, *oth = tmp;
+    double acc = wp.sweep(cur, rhs, oth, nx, k);  // sweep 1: u -> tmp
+    __syncwarp();
+    { double *t_ = cur; cur = oth; oth = t_; }
+    double tot = 0.0;
+    int s = 1;
+    for (;; ++s) {
+        double acc_next = 0.0;
+        if (s < iters) acc_next = wp.sweep(cur, rhs, oth, nx, k);  // speculative sweep s+1
+        tot = warp_sum(acc);
+        if (tot < sstar || s >= iters) break;
+        __syncwarp();
+        { double *t_ = cur; cur = oth; oth = t_; }
+        acc = acc_next;
+    }
+    __syncwarp();
+    if (cur != u) {
+        for (int q = threadIdx.x & 31; q < n; q += 32) u[q] = cur[q];
+        __syncwarp();
+    }
+    if (sweeps_out != nullptr && (threadIdx.x & 31) == 0) *sweeps_out = s;
+    return tot;
+}
+
 // Coarsest-level solve (multigrid.jl:145-167). u in place; tmp = scratch of the level; work = CG scratch.
 template <class G>
 __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const double *rhs, double *tmp, double *work, int nx,
@@ -1042,8 +1127,16 @@ __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const doubl
     const int n = nx * ny;
     double ss = 0.0;
     if (a.coarse_solver == B2S_COARSE_JACOBI) {
-        const double tol_rhs = tol * sqrt(sm_sumsq(g, rhs, n) / ((double)nx * ny));
+        const double N = (double)nx * ny;
+        const double tol_rhs = tol * sqrt(sm_sumsq(g, rhs, n) / N);
+        const double sstar = exit_threshold(tol_rhs, N);  // res_rms < tol_rhs  <=>  ss < sstar
         const Coef k = make_coef(h, c, 4.0 / 5.0);
+        if (a.smoother == B2S_SMOOTH_JACOBI && g.size() == 32 && n <= 128) {
+            if (n <= 32) return warp_coarsest_jacobi<1>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);
+            if (n <= 64) return warp_coarsest_jacobi<2>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);
+            if (n <= 96) return warp_coarsest_jacobi<3>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);
+            return warp_coarsest_jacobi<4>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);
+        }
         int sweeps = 0;
         double *src = u, *dst = tmp;
         for (int s = 1; s <= iters; ++s) {
@@ -1054,7 +1147,7 @@ __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const doubl
                 double *t = src; src = dst; dst = t;
             }
             ++sweeps;
-            if (sqrt(ss / ((double)nx * ny)) < tol_rhs) break;
+            if (ss < sstar) break;
         }
         if (src != u) {  // odd number of Jacobi sweeps: result sits in tmp
             for (int p = g.rank(); p < n; p += g.size()) u[p] = src[p];
