@@ -55,6 +55,10 @@ struct b2s_mg {
     int tile_choice = 0;
     int stream_ch = 0;
     long long *prof_dev = nullptr;  // B2S_MG_PROF=1: phase stamps of the collapsed coarse kernel
+    bool coarse_global = false;     // coarsest level too large for shared memory: solved by global-memory kernels
+    CoarseLoop *loop_dev = nullptr, *loop_pin = nullptr;
+    double *cg_work = nullptr;      // 4 arrays of the coarsest size (global CG)
+    int last_sweeps_host = -1;
 };
 
 namespace {
@@ -95,6 +99,10 @@ cudaError_t tile_set_attr(int choice)
     case 3: return tile_set_attr_t<128, 16>();
     }
 }
+
+int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count);
+int cg_global(double *x_in, const double *b, double *work, double hx, double hy, double c, double tol, int nmax, int nx, int ny,
+              cudaStream_t st, double *ss_out, int *iters_out, long long *count);
 
 // Enqueues one V-cycle (multigrid.jl:91-170) on `st`; counts kernel launches.
 int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
@@ -142,7 +150,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
             }
         }
     };
-    const int fs = h->first_smem;
+    const int fs = h->coarse_global ? h->nlev - 1 : h->first_smem;
     const bool fused = c.fuse_sweeps && !rb && c.restriction == B2S_RESTRICT_INJECT;
     auto tile_args = [&](int l) {
         TileArgs t = {};
@@ -188,6 +196,12 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         mg_restrict_kernel<<<g, dim3(64, 4, 1), 0, st>>>(r);
         ++n;
     }
+    // coarsest level in global memory (too large for shared memory)
+    if (h->coarse_global) {
+        long long nn = 0;
+        B2S_CHECK(coarse_global_solve(h, st, &nn));
+        n += nn;
+    } else
     // collapsed coarse hierarchy
     {
         CoarseArgs a = {};
@@ -246,6 +260,106 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     return B2S_OK;
 }
 
+// cg!(x_in, b, hx, hy, c, tol, Nmax) with global-memory kernels, host-driven like the reference (krylov.jl:55-91).
+// work: 4*nx*ny doubles. Synchronises `st`.
+int cg_global(double *x_in, const double *b, double *work, double hx, double hy, double c, double tol, int nmax, int nx, int ny,
+              cudaStream_t st, double *ss_out, int *iters_out, long long *count)
+{
+    const size_t n = (size_t)nx * ny, bytes = n * sizeof(double);
+    double *r = work, *p = work + n, *ph = work + 2 * n, *x = work + 3 * n;
+    long long nl = 0;
+    double v = 0.0;
+    B2S_CHECK(b2s_sumsq(b, n, &v, st)); ++nl;
+    const double normb = sqrt(v), tolb = tol * normb;
+    B2S_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(p, b, bytes, cudaMemcpyDeviceToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(ph, b, bytes, cudaMemcpyDeviceToDevice, st));
+    B2S_CUDA(cudaMemsetAsync(x, 0, bytes, st));
+    double rho = 0.0;
+    B2S_CHECK(b2s_dot(r, r, n, &rho, st)); ++nl;
+    int it = 0;
+    double rr = rho;
+    for (int k = 1; k <= nmax; ++k) {
+        it = k;
+        B2S_CHECK(b2s_matvec2d(p, hx, hy, c, ph, nx, ny, B2S_POLICY_PARALLEL, st));
+        double pAp = 0.0;
+        B2S_CHECK(b2s_dot(p, ph, n, &pAp, st));
+        const double alpha = rho / pAp;
+        B2S_CHECK(b2s_axpy(alpha, p, x, n, st));
+        B2S_CHECK(b2s_axpy(-alpha, ph, r, n, st));  // r .-= alpha .* p_hat  (r + (-alpha)*ph == r - alpha*ph exactly)
+        B2S_CHECK(b2s_sumsq(r, n, &rr, st));
+        nl += 5;
+        if (sqrt(rr) < tolb) break;
+        const double rho_old = rho;
+        rho = rr;
+        const double beta = rho / rho_old;
+        B2S_CHECK(b2s_xpby(r, beta, p, n, st)); ++nl;
+    }
+    B2S_CUDA(cudaMemcpyAsync(x_in, x, bytes, cudaMemcpyDeviceToDevice, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (ss_out) *ss_out = rr;
+    if (iters_out) *iters_out = it;
+    if (count) *count = nl;
+    return B2S_OK;
+}
+
+// Coarsest-level solve in global memory (multigrid.jl:145-167) for levels that do not fit into shared memory:
+// Jacobi sweeps with the exit test on the device, launched in batches and polled; or the host-driven CG above.
+int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count)
+{
+    const int l = h->nlev - 1;
+    const int nx = h->nx[l], ny = h->ny[l];
+    const size_t n = (size_t)nx * ny;
+    const MGCall &m = *h->call_pin;
+    double hl = m.h;
+    for (int i = 0; i < l; ++i) hl = hl * 2;
+    double *u = l == 0 ? m.u : h->u[l];
+    const double *rhs = l == 0 ? m.rhs : h->rhs[l];
+    const int iters = 20 * h->cfg.coarse_solve_size;
+    long long nl = 0;
+    if (h->cfg.coarse_solver == B2S_COARSE_CG) {
+        double ss = 0.0;
+        int it = 0;
+        long long c2 = 0;
+        B2S_CHECK(cg_global(u, rhs, h->cg_work, hl, hl, m.c, m.tol, iters, nx, ny, st, &ss, &it, &c2));
+        nl += c2;
+        h->last_sweeps_host = it;
+        if (l == 0) B2S_CUDA(cudaMemcpyAsync(h->sumsq_dev, &ss, sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        mg_reduce_kernel<<<kReduceBlocks, kReduceThreads, 0, st>>>(rhs, rhs, n, h->partials, h->ticket, h->sumsq_dev + 4, nullptr, 0);
+        mg_coarse_loop_init_kernel<<<1, 32, 0, st>>>(h->loop_dev, h->sumsq_dev + 4, h->call_dev, (double)nx * ny, iters);
+        nl += 2;
+        const int rows = rows_for(nx, ny);
+        int launched = 0;
+        CoarseLoop cur = {};
+        while (!cur.done) {
+            const int batch = std::min(32, iters - launched);
+            for (int k = 0; k < batch; ++k, ++launched) {
+                SweepArgs a = {};
+                a.nx = nx; a.ny = ny; a.rows = rows; a.h = hl; a.c = m.c; a.alpha = 4.0 / 5.0; a.mode = 1;
+                a.rhs = rhs;
+                a.u = (launched & 1) ? h->tmp[l] : u;
+                a.out = (launched & 1) ? u : h->tmp[l];
+                a.want_norm = 1; a.partials = h->partials; a.ticket = h->ticket; a.sumsq_out = h->sumsq_dev;
+                a.loop = h->loop_dev;
+                mg_sweep_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, st>>>(a);
+                ++nl;
+            }
+            B2S_CUDA(cudaGetLastError());
+            B2S_CUDA(cudaMemcpyAsync(h->loop_pin, h->loop_dev, sizeof(CoarseLoop), cudaMemcpyDeviceToHost, st));
+            B2S_CUDA(cudaStreamSynchronize(st));
+            cur = *h->loop_pin;
+            launched = cur.sweeps;  // launches after the exit were no-ops
+            if (launched >= iters) break;
+        }
+        if (cur.sweeps & 1)  // odd number of sweeps: the result sits in tmp
+            B2S_CUDA(cudaMemcpyAsync(u, h->tmp[l], n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        h->last_sweeps_host = cur.sweeps;
+    }
+    if (count) *count = nl;
+    return B2S_OK;
+}
+
 int launch_cycle(b2s_mg *h)
 {
     if (h->cfg.use_graph) {
@@ -299,6 +413,9 @@ int mg_destroy_impl(b2s_mg *h)
     if (h->partials) cudaFree(h->partials);
     if (h->ticket) cudaFree(h->ticket);
     if (h->prof_dev) cudaFree(h->prof_dev);
+    if (h->loop_dev) cudaFree(h->loop_dev);
+    if (h->loop_pin) cudaFreeHost(h->loop_pin);
+    if (h->cg_work) cudaFree(h->cg_work);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -368,10 +485,16 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
             bytes += add;
             fs = l;
         }
-        if (fs == L) {
-            set_error("coarsest level %dx%d does not fit into shared memory (not implemented)", h->nx[L - 1], h->ny[L - 1]);
-            delete h;
-            return B2S_ERR_NOT_IMPLEMENTED;
+        if (fs == L) {  // coarsest level does not fit into shared memory: global-memory coarsest solve, host-polled
+            if (cfg->smoother == B2S_SMOOTH_RBGS && cfg->coarse_solver == B2S_COARSE_JACOBI) {
+                set_error("coarsest level %dx%d with the red-black smoother does not fit into shared memory (not implemented)",
+                          h->nx[L - 1], h->ny[L - 1]);
+                delete h;
+                return B2S_ERR_NOT_IMPLEMENTED;
+            }
+            h->coarse_global = true;
+            h->cfg.use_graph = 0;  // the coarsest solve polls the device between batches of sweeps
+            bytes = 0;
         }
         h->first_smem = fs;
         h->coarse_smem = bytes;
@@ -396,12 +519,18 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
             MG_CUDA(cudaMalloc(&h->tmp[l], bytes));
             MG_CUDA(cudaMemset(h->tmp[l], 0, bytes));
         }
-        if (l >= 1 && l <= h->first_smem) {
+        if (l >= 1 && l <= h->first_smem && l < L) {
             MG_CUDA(cudaMalloc(&h->u[l], bytes));
             MG_CUDA(cudaMalloc(&h->rhs[l], bytes));
             MG_CUDA(cudaMemset(h->u[l], 0, bytes));
             MG_CUDA(cudaMemset(h->rhs[l], 0, bytes));
         }
+    }
+    if (h->coarse_global) {
+        MG_CUDA(cudaMalloc(&h->loop_dev, sizeof(CoarseLoop)));
+        MG_CUDA(cudaMallocHost(&h->loop_pin, sizeof(CoarseLoop)));
+        if (cfg->coarse_solver == B2S_COARSE_CG)
+            MG_CUDA(cudaMalloc(&h->cg_work, 4 * (size_t)h->nx[L - 1] * h->ny[L - 1] * sizeof(double)));
     }
     MG_CUDA(cudaMalloc(&h->call_dev, sizeof(MGCall)));
     MG_CUDA(cudaMallocHost(&h->call_pin, sizeof(MGCall)));
@@ -528,6 +657,7 @@ int b2s_mg_last_coarse_sweeps(const b2s_mg *h, int *sweeps)
     DeviceGuard guard;
     guard.set(h->cfg.device);
     B2S_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->coarse_global) { *sweeps = h->last_sweeps_host; return B2S_OK; }
     B2S_CUDA(cudaMemcpy(sweeps, h->sweeps_dev, sizeof(int), cudaMemcpyDeviceToHost));
     return B2S_OK;
 }
@@ -696,11 +826,21 @@ int b2s_cg_solve(double *x, const double *b, double hx, double hy, double c, dou
     B2S_CHECK(check_policy(policy));
     const size_t n = (size_t)nx * ny;
     const size_t smem = 6 * n * sizeof(double);
-    B2S_REQUIRE(smem <= 220 * 1024, B2S_ERR_NOT_IMPLEMENTED,
-                "stand-alone cg! is implemented for grids of up to %d points (got %dx%d)", (int)(220 * 1024 / 48), nx, ny);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (smem > 220 * 1024) {  // larger than shared memory: host-driven global-memory CG (3 syncs per iteration, like the reference)
+        double *work = nullptr;
+        B2S_CUDA(cudaMalloc(&work, 4 * n * sizeof(double)));
+        double ss = 0.0;
+        int it = 0;
+        const int rc = cg_global(x, b, work, hx, hy, c, tol, nmax, nx, ny, st, &ss, &it, nullptr);
+        cudaFree(work);
+        if (rc != B2S_OK) return rc;
+        if (res_rms) *res_rms = sqrt(ss / ((double)nx * ny));
+        if (iters) *iters = it;
+        return B2S_OK;
+    }
     Scratch *sc = nullptr;
     B2S_CHECK(get_scratch(&sc));
-    cudaStream_t st = (cudaStream_t)stream;
     static bool attr = false;
     if (!attr) {
         B2S_CUDA(cudaFuncSetAttribute(mg_cg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -59,6 +59,12 @@ __device__ __forceinline__ double point_residual(const double *__restrict__ u, c
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMGBX = 128;
 
+// Device-resident state of a coarsest-level Jacobi solve that runs in global memory (level too large for shared memory)
+struct CoarseLoop {
+    double sstar;   // exit threshold on sum res^2 (exit_threshold)
+    int sweeps, done, iters, pad;
+};
+
 struct SweepArgs {
     const MGCall *cp;
     int level;          // 0: arrays come from *cp
@@ -73,11 +79,13 @@ struct SweepArgs {
     unsigned int *ticket;
     double *sumsq_out;
     int swap_io;        // level 0 ping-pong: 1 -> read tmp (u arg), write cp->u
+    CoarseLoop *loop;   // nullable: global-memory coarsest solve -- skip when done, run the exit test in the last block
 };
 
 __global__ void __launch_bounds__(kMGBX) mg_sweep_kernel(const SweepArgs a)
 {
     __shared__ double red[32];
+    if (a.loop != nullptr && a.loop->done) return;
     const double *u = a.u;
     const double *rhs = a.rhs;
     double *out = a.out;
@@ -115,7 +123,14 @@ __global__ void __launch_bounds__(kMGBX) mg_sweep_kernel(const SweepArgs a)
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
         const double bsum = block_sum(acc, red);
         double total;
-        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) {
+            *a.sumsq_out = total;
+            if (a.loop != nullptr) {  // res_rms < tol_rhs -> break   (multigrid.jl:150-156)
+                const int sw = a.loop->sweeps + 1;
+                a.loop->sweeps = sw;
+                if (total < a.loop->sstar || sw >= a.loop->iters) a.loop->done = 1;
+            }
+        }
     }
 }
 
@@ -1261,6 +1276,18 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
     }
     __syncthreads();
     coarse_stamp(a);
+}
+
+// tol_rhs = tol * sqrt(sum(rhs.^2)/(nx*ny)) and the exit threshold of a global-memory coarsest Jacobi solve
+__global__ void mg_coarse_loop_init_kernel(CoarseLoop *loop, const double *sumsq_rhs, const MGCall *cp, double N, int iters)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double tol_rhs = cp->tol * sqrt(*sumsq_rhs / N);
+        loop->sstar = exit_threshold(tol_rhs, N);
+        loop->sweeps = 0;
+        loop->done = 0;
+        loop->iters = iters;
+    }
 }
 
 // Stand-alone CG for grids that fit into shared memory (test/krylov.jl shape: 66^2).

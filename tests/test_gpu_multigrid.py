@@ -168,6 +168,44 @@ def test_mgsolve_bench_shape_counts(p2, oracle, n, cs, solver):
     hd.close()
 
 
+@pytest.mark.parametrize("solver", [0, 1])
+def test_large_coarsest_level_in_global_memory(p2, oracle, solver):
+    """multigrid_bench.jl sweeps coarse sizes up to 2^8+1: a 129^2 coarsest level does not fit into shared memory and
+    is solved by global-memory kernels (Jacobi with the device-side exit test, or host-driven CG)."""
+    n, cs = 257, 129
+    h = 1.0 / (n - 1)
+    b = rnd((n, n), 3)
+    opt_o = oracle.MGOpt(coarse_solve_size=cs, coarse_solver=solver)
+    xo = oracle.farray((n, n))
+    r_o, nc_o, hist_o = oracle.mgsolve2d(xo, b, h, 0.0, 1e-6, 20, opt=opt_o)
+    sw_o = oracle.lib().orc_mg_last_coarse_sweeps()
+    x = p2.zeros(n, n)
+    hd = p2.preallocate_buffers(n, n, p2.MGOpt(coarse_solve_size=cs, coarse_solver=solver))
+    r_g, nc_g, hist_g = hd.solve(x, p2.to_device(b), h, 0.0, 1e-6, 20, False, want_hist=True)
+    assert nc_g == nc_o
+    assert hd.last_coarse_sweeps() == sw_o
+    assert np.allclose(hist_g, hist_o, rtol=1e-9 if solver == 0 else 1e-5, atol=0)
+    got = p2.to_host(x)
+    if solver == 0:
+        assert np.array_equal(got, xo)
+    else:
+        assert np.max(np.abs(got - xo)) <= 1e-8 * np.max(np.abs(xo))
+    hd.close()
+
+
+def test_cg_larger_than_shared_memory(p2, oracle):
+    n, c = 130, 3.14
+    h = 1.0 / (n - 1)
+    b = np.zeros((n, n), order="F"); b[1:-1, 1:-1] = rnd((n - 2, n - 2), 4)
+    x = p2.zeros(n, n)
+    r, it = p2.cg(x, p2.to_device(b), h, h, c, 1e-6, 2000, return_iters=True)
+    xo = oracle.farray((n, n))
+    r_o, it_o = oracle.cg2d(xo, b, h, h, c, 1e-6, 2000)
+    assert it == it_o and r < 1e-6 * np.sqrt(np.sum(b ** 2) / n ** 2)
+    assert abs(r - r_o) <= 1e-5 * r_o
+    assert np.max(np.abs(p2.to_host(x) - xo)) <= 1e-8 * np.max(np.abs(xo))
+
+
 def test_variant_b_five_cycles(p2, oracle):
     n = 1025
     b = rnd((n, n), 1)
