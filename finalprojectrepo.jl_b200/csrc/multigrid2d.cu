@@ -160,7 +160,14 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     };
     const int tile_choice = h->tile_choice;
     // downward leg on the global-memory levels
-    const bool streaming = c.fuse_sweeps != 2;
+    // fuse_sweeps: 1 = automatic (streaming kernels for large levels, where their lower instruction count wins; tile
+    // kernels for levels <= ~1.5 M points, which are latency-bound and prefer 3 barriers to a 24-step pipeline),
+    // 2 = tiles everywhere, 3 = streaming everywhere
+    auto use_streaming = [&](int l) {
+        if (c.fuse_sweeps == 2) return false;
+        if (c.fuse_sweeps == 3) return true;
+        return (size_t)h->nx[l] * h->ny[l] > (size_t)1500000;
+    };
     auto stream_rows = [&](int l) {
         // rows per chunk (even, >= 16, <= ~256): the grid should fill whole waves of 148 SMs x 6 resident blocks
         const int bx = (h->nx[l] + kSW - 1) / kSW, ny = h->ny[l], slots = 148 * 6;
@@ -178,7 +185,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = 0; l < fs && fused; ++l) {
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
-        if (streaming) {
+        if (use_streaming(l)) {
             const int ch = stream_rows(l);
             mg_down_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
         } else {
@@ -221,7 +228,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        if (streaming) {
+        if (use_streaming(l)) {
             const int ch = stream_rows(l);
             mg_up_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
         } else {

@@ -209,8 +209,8 @@ typedef struct {
     int use_graph;         /* 1: V-cycle captured once in a CUDA graph and replayed */
     int smem_levels;       /* 1: all levels that fit are collapsed into one shared-memory-resident kernel */
     int fuse_sweeps;       /* temporal blocking on the fine levels (2 sweeps + transfer operator per kernel; variant A
-                              only, bit-identical to the unfused kernels): 0 off, 1 streaming y-marching kernels,
-                              2 shared-memory tile kernels */
+                              only, bit-identical to the unfused kernels): 0 off, 1 automatic (streaming y-marching
+                              kernels on large levels, shared-memory tile kernels on small ones), 2 tiles, 3 streaming */
 } b2s_mg_config;
 
 /* preallocate_buffers(nx, ny)  multigrid.jl:25-38 (+ level table, graphs). */

@@ -104,6 +104,7 @@ CONFIGS = [
     dict(),                                             # defaults: graph + collapsed coarse + fused tiles, cs=5, Jacobi
     dict(fuse_sweeps=False),                            # one kernel per sweep / transfer operator
     dict(fuse_sweeps=2),                                # shared-memory tile variant of the fused level kernels
+    dict(fuse_sweeps=3),                                # streaming variant on every level
     dict(use_graph=False),
     dict(use_graph=False, fuse_sweeps=False, smem_levels=False),
     dict(smem_levels=False),
@@ -315,13 +316,13 @@ def test_full_size_properties(p2):
         b = rnd((n, n), 1)
         db = p2.to_device(b)
         outs = []
-        for use_graph, fuse in ((True, 1), (False, 2), (True, 0)):
+        for use_graph, fuse in ((True, 1), (False, 2), (True, 0), (True, 3)):
             x = p2.zeros(n, n)
             r, nc = p2.MGsolve_2DPoisson(x, db, 1.0 / (n - 1), 0.0, 1e-6, 100, False,
                                          opt=p2.MGOpt(use_graph=use_graph, fuse_sweeps=fuse), return_cycles=True)
             assert nc == 7 and r < 1e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
             outs.append(p2.to_host(x))
-        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        assert all(np.array_equal(outs[0], o) for o in outs[1:])
         # the discrete equation holds to the solver tolerance on the interior
         x = outs[0]
         lap = (x[2:, 1:-1] + x[:-2, 1:-1] + x[1:-1, 2:] + x[1:-1, :-2] - 4 * x[1:-1, 1:-1]) * (n - 1) ** 2
