@@ -58,6 +58,7 @@ struct b2s_mg {
     bool coarse_global = false;     // coarsest level too large for shared memory: solved by global-memory kernels
     CoarseLoop *loop_dev = nullptr, *loop_pin = nullptr;
     double *cg_work = nullptr;      // 4 arrays of the coarsest size (global CG)
+    double *pcg_work = nullptr;     // 4 arrays of the finest size (MG-preconditioned CG), allocated on first use
     int last_sweeps_host = -1;
 };
 
@@ -423,6 +424,7 @@ int mg_destroy_impl(b2s_mg *h)
     if (h->loop_dev) cudaFree(h->loop_dev);
     if (h->loop_pin) cudaFreeHost(h->loop_pin);
     if (h->cg_work) cudaFree(h->cg_work);
+    if (h->pcg_work) cudaFree(h->pcg_work);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -655,6 +657,63 @@ int b2s_mg_cycles(b2s_mg *h, double *u, const double *f, double hgrid, double c,
     h->last_ms = ms;
     if (ms_out) *ms_out = ms;
     if (r_rms_last) *r_rms_last = sqrt(h->sumsq_pin[0] / ((double)h->nx[0] * h->ny[0]));
+    return B2S_OK;
+}
+
+int b2s_mg_pcg_solve(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int maxit, double *r_rms_out,
+                     int *iters_out)
+{
+    B2S_REQUIRE(h && u && f && maxit >= 0, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_REQUIRE(h->cfg.restriction == B2S_RESTRICT_FW, B2S_ERR_BAD_ARG,
+                "MG-preconditioned CG needs a symmetric V-cycle: use restriction = B2S_RESTRICT_FW");
+    DeviceGuard guard;
+    guard.set(h->cfg.device);
+    const int nx = h->nx[0], ny = h->ny[0];
+    const size_t n = (size_t)nx * ny, bytes = n * sizeof(double);
+    if (!h->pcg_work) B2S_CUDA(cudaMalloc(&h->pcg_work, 4 * bytes));
+    double *r = h->pcg_work, *z = r + n, *p = r + 2 * n, *q = r + 3 * n;
+    cudaStream_t st = h->stream;
+    const double N = (double)nx * ny;
+    const int rows = rows_for(nx, ny);
+    B2S_CUDA(cudaEventRecord(h->ev0, st));
+    B2S_CUDA(cudaMemsetAsync(q, 0, bytes, st));
+    B2S_CHECK(b2s_matvec2d(u, hgrid, hgrid, c, q, nx, ny, B2S_POLICY_PARALLEL, st));
+    mg_pcg_residual_kernel<<<sweep_grid(nx, ny, rows), kMGBX, 0, st>>>(f, q, r, nx, ny, rows);
+    B2S_CUDA(cudaGetLastError());
+    double ss = 0.0;
+    B2S_CHECK(b2s_sumsq(r, n, &ss, st));
+    h->kernel_launches += 3;
+    double r_rms = sqrt(ss / N);
+    const double tolf = tol * r_rms;
+    int it = 0;
+    double rz = 0.0;
+    for (int k = 1; k <= maxit && r_rms >= tolf && r_rms > 0.0; ++k) {
+        it = k;
+        B2S_CUDA(cudaMemsetAsync(z, 0, bytes, st));
+        B2S_CHECK(b2s_mg_vcycle(h, z, r, hgrid, c, tol, 0, nullptr));  // z = M r
+        double rz_new = 0.0;
+        B2S_CHECK(b2s_dot(r, z, n, &rz_new, st));
+        if (k == 1) B2S_CUDA(cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, st));
+        else B2S_CHECK(b2s_xpby(z, rz_new / rz, p, n, st));  // p = z + beta p
+        rz = rz_new;
+        B2S_CUDA(cudaMemsetAsync(q, 0, bytes, st));
+        B2S_CHECK(b2s_matvec2d(p, hgrid, hgrid, c, q, nx, ny, B2S_POLICY_PARALLEL, st));
+        double pq = 0.0;
+        B2S_CHECK(b2s_dot(p, q, n, &pq, st));
+        const double alpha = rz / pq;
+        B2S_CHECK(b2s_axpy(alpha, p, u, n, st));
+        B2S_CHECK(b2s_axpy(-alpha, q, r, n, st));
+        B2S_CHECK(b2s_sumsq(r, n, &ss, st));
+        h->kernel_launches += 7;
+        r_rms = sqrt(ss / N);
+    }
+    B2S_CUDA(cudaEventRecord(h->ev1, st));
+    B2S_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    B2S_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    if (r_rms_out) *r_rms_out = r_rms;
+    if (iters_out) *iters_out = it;
     return B2S_OK;
 }
 

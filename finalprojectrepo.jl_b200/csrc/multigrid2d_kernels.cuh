@@ -847,6 +847,19 @@ __global__ void __launch_bounds__(kMGBX) mg_matvec_kernel(const double *__restri
     }
 }
 
+// r = f - q on the interior, 0 on the frame (initial residual of the MG-preconditioned CG)
+__global__ void __launch_bounds__(kMGBX) mg_pcg_residual_kernel(const double *__restrict__ f, const double *__restrict__ q,
+                                                                double *__restrict__ r, int nx, int ny, int rows)
+{
+    const int i = blockIdx.x * kMGBX + threadIdx.x;
+    if (i >= nx) return;
+    const int j0 = blockIdx.y * rows, j1 = min(j0 + rows, ny);
+    for (int j = j0; j < j1; ++j) {
+        const size_t p = (size_t)i + (size_t)nx * j;
+        r[p] = (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) ? f[p] - q[p] : 0.0;
+    }
+}
+
 // Deterministic reductions / vector updates of cg! and of the residual checks.
 // op 0: sum x*y ; op 1: sum x*x.  Fixed grid (kReduceBlocks) -> fixed summation order.
 constexpr int kReduceBlocks = 296, kReduceThreads = 256;

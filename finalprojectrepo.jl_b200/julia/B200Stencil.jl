@@ -162,6 +162,17 @@ function MGsolve_2DPoisson!(u::CuArray{Float64,2}, f::CuArray{Float64,2}, h::Flo
     return r[]
 end
 
+"""MG-preconditioned CG (extension, no counterpart in the reference): (r_rms, iterations). The handle must have been
+created with full-weighting restriction (MGConfig.restriction = 1)."""
+function mg_pcg!(hd::MGHandle, u::CuArray{Float64,2}, f::CuArray{Float64,2}, h::Float64, c::Float64, tol::Float64, maxit::Int)
+    CUDA.synchronize()
+    r = Ref{Cdouble}(0.0); it = Ref{Cint}(0)
+    check(ccall((:b2s_mg_pcg_solve, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, Cdouble, Cdouble, Cdouble, Cint, Ref{Cdouble}, Ref{Cint}),
+                hd.ptr, u, f, h, c, tol, maxit, r, it))
+    return r[], Int(it[])
+end
+
 """res_rms = cg!(x_in, b, hx, hy, c, tol, Nmax; execution_policy, verbose)  (krylov.jl:55-91)"""
 function cg!(x_in::CuArray{Float64,2}, b::CuArray{Float64,2}, hx, hy, c, tol, Nmax; execution_policy=parallel_shmem,
              verbose=false)

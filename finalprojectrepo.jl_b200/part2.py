@@ -125,6 +125,14 @@ class MGHandle:
                                          C.byref(r), C.byref(ms)))
         return r.value, ms.value
 
+    def pcg(self, u, f, h, c, tol, maxit):
+        """MG-preconditioned CG (extension): returns (r_rms, iterations)."""
+        assert _chk(u) == (self.nx, self.ny) and _chk(f) == (self.nx, self.ny)
+        _torch().cuda.current_stream().synchronize()
+        r, it = C.c_double(), C.c_int()
+        capi.check(self._L.b2s_mg_pcg_solve(self._h, capi.ptr(u), capi.ptr(f), h, c, tol, int(maxit), C.byref(r), C.byref(it)))
+        return r.value, it.value
+
     def last_coarse_sweeps(self):
         n = C.c_int()
         capi.check(self._L.b2s_mg_last_coarse_sweeps(self._h, C.byref(n)))

@@ -227,6 +227,13 @@ int b2s_mg_vcycle(b2s_mg *h, double *u_dev, const double *rhs_dev, double hgrid,
 /* Fixed number of V-cycles without the exit test (benchmark). Device time of the call in *ms (CUDA events). */
 int b2s_mg_cycles(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, double c, double tol, int ncycles,
                   int apply_bcs, double *r_rms_last, double *ms);
+/* MG-preconditioned CG (north-star extension; the reference has no such solver): solves
+ * (lap - c) u = f on the interior (frame of u = Dirichlet data) by CG on matrix_free_matvec_prod! (krylov.jl:7-13) with
+ * ONE V-cycle of this handle (started from zero) as preconditioner. Needs a symmetric cycle: restriction must be
+ * B2S_RESTRICT_FW (with injection the V-cycle is not symmetric and CG stagnates -> B2S_ERR_BAD_ARG).
+ * Exit: sqrt(sum r^2/(nx ny)) < tol * (the same norm of the initial residual). iters = CG iterations = V-cycles. */
+int b2s_mg_pcg_solve(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, double c, double tol, int maxit,
+                     double *r_rms, int *iters);
 /* Sweeps / iterations the coarsest-level solver used in the last V-cycle. */
 int b2s_mg_last_coarse_sweeps(const b2s_mg *h, int *sweeps);
 int b2s_mg_stats(const b2s_mg *h, long long *kernel_launches, double *last_call_ms);

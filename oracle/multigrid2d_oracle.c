@@ -470,3 +470,46 @@ void orc_ns_step(const orc_ns_params *P, const orc_mg_opt *o, double *S, double 
     free(vx); free(vy); free(v); free(dT2); free(dTx); free(dTy); free(dW2); free(dWx); free(dWy);
     free(Ra_dTdx); free(rhs);
 }
+
+/* ------------------------------------------------------------------------- */
+/* MG-preconditioned CG (north-star extension): NO reference implementation -- "parity unpinned";   */
+/* this restatement is the only definition the CUDA path (b2s_mg_pcg_solve) is checked against.                       */
+/* Solves (lap - c) u = f on the interior (frame of u = Dirichlet data) with CG preconditioned by ONE V-cycle of the  */
+/* configured variant started from zero. The operator is applied with matrix_free_matvec_prod! (krylov.jl:7-13),      */
+/* dots as in cg! (krylov.jl:64-83); exit when sqrt(sum r^2/(nx ny)) < tol * sqrt(sum f_interior^2/(nx ny)).          */
+/* ------------------------------------------------------------------------- */
+double orc_mg_pcg2d(double *u, const double *f, double h, double c, double tol, int maxit, int nx, int ny,
+                    const orc_mg_opt *o, int *iters_out)
+{
+    size_t n = (size_t)nx * ny;
+    double *r = (double *)calloc(n, 8), *z = (double *)calloc(n, 8), *p = (double *)calloc(n, 8), *q = (double *)calloc(n, 8);
+    orc_matvec2d(u, h, h, c, q, nx, ny);
+    for (int j = 1; j < ny - 1; ++j)
+        for (int i = 1; i < nx - 1; ++i) r[IDX(i, j)] = f[IDX(i, j)] - q[IDX(i, j)];
+    const double N = (double)nx * ny;
+    const double tolf = tol * sqrt(sumsq(r, nx, ny) / N);  /* relative to the initial residual */
+    double r_rms = sqrt(sumsq(r, nx, ny) / N);
+    int it = 0;
+    double rz = 0.0;
+    for (int k = 1; k <= maxit && r_rms >= tolf && r_rms > 0.0; ++k) {
+        it = k;
+        memset(z, 0, n * 8);
+        orc_vcycle2d(z, r, h, c, tol, nx, ny, 0, o);
+        double rz_new = dot(r, z, nx, ny);
+        if (k == 1) memcpy(p, z, n * 8);
+        else {
+            double beta = rz_new / rz;
+            for (size_t t = 0; t < n; ++t) p[t] = z[t] + beta * p[t];
+        }
+        rz = rz_new;
+        memset(q, 0, n * 8);
+        orc_matvec2d(p, h, h, c, q, nx, ny);
+        double alpha = rz / dot(p, q, nx, ny);
+        for (size_t t = 0; t < n; ++t) u[t] += alpha * p[t];
+        for (size_t t = 0; t < n; ++t) r[t] -= alpha * q[t];
+        r_rms = sqrt(sumsq(r, nx, ny) / N);
+    }
+    free(r); free(z); free(p); free(q);
+    if (iters_out) *iters_out = it;
+    return r_rms;
+}

@@ -104,6 +104,8 @@ def lib():
         L.orc_mgsolve2d.restype = C.c_double
         L.orc_mgsolve2d.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(MGOpt), _ip, _dp]
+        L.orc_mg_pcg2d.restype = C.c_double
+        L.orc_mg_pcg2d.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(MGOpt), _ip]
         L.orc_ns_init_cosine.argtypes = [_dp, C.c_int, C.c_int]
         L.orc_ns_step.argtypes = [C.POINTER(NSParams), C.POINTER(MGOpt), _dp, _dp, _dp, C.POINTER(NSStepInfo), _dp]
         _LIB = L
@@ -242,6 +244,14 @@ def mgsolve2d(u, f, h, c, tol, niters, apply_BCs=False, opt=None):
     r = lib().orc_mgsolve2d(_p(u), _p(f), h, c, tol, niters, int(apply_BCs), u.shape[0], u.shape[1], C.byref(opt),
                             C.byref(nc), hist.ctypes.data_as(_dp))
     return r, nc.value, hist[:nc.value]
+
+
+def mg_pcg2d(u, f, h, c, tol, maxit, opt=None):
+    """Returns (r_rms, iterations)."""
+    opt = opt or MGOpt()
+    it = C.c_int()
+    r = lib().orc_mg_pcg2d(_p(u), _p(f), h, c, tol, maxit, u.shape[0], u.shape[1], C.byref(opt), C.byref(it))
+    return r, it.value
 
 
 def ns_step(params, S, T, W, opt=None, want_aux=False):

@@ -219,6 +219,28 @@ def test_variant_b_five_cycles(p2, oracle):
     assert np.array_equal(p2.to_host(x), xo)
 
 
+@pytest.mark.parametrize("cfg", [dict(restriction=1), dict(smoother=1, restriction=1)], ids=["jacobi+fw", "rbgs+fw"])
+def test_mg_preconditioned_cg(p2, oracle, cfg):
+    """MG-preconditioned CG (north-star extension; no reference implementation -> checked against the oracle only)."""
+    from b200stencil import capi
+    n = 513
+    h = 1.0 / (n - 1)
+    b = rnd((n, n), 1)
+    xo = oracle.farray((n, n))
+    r_o, it_o = oracle.mg_pcg2d(xo, b, h, 0.0, 1e-6, 50, oracle.MGOpt(smoother=cfg.get("smoother", 0), restriction=1))
+    x = p2.zeros(n, n)
+    hd = p2.preallocate_buffers(n, n, p2.MGOpt(**cfg))
+    r_g, it_g = hd.pcg(x, p2.to_device(b), h, 0.0, 1e-6, 50)
+    assert it_g == it_o and it_g <= 8
+    assert abs(r_g - r_o) <= 1e-6 * r_o
+    assert np.max(np.abs(p2.to_host(x) - xo)) <= 1e-9 * np.max(np.abs(xo))
+    hd.close()
+    bad = p2.preallocate_buffers(n, n, p2.MGOpt())  # injection: the cycle is not symmetric
+    with pytest.raises(capi.B2SError):
+        bad.pcg(p2.zeros(n, n), p2.to_device(b), h, 0.0, 1e-6, 5)
+    bad.close()
+
+
 def test_fortran_golden_poisson_and_explicit_step(p2, oracle):
     """test/part2.jl: navier_stokes_2D(testmode) at 257x65, tol 1e-12, W from Winit.bin vs {T,W,S}.bin, atol 1e-8."""
     Winit = p2.load(os.path.join(F, "Winit.bin"))

@@ -148,6 +148,21 @@ def test_variant_b_and_rejected_combinations(oracle):
     assert nc == 30 and not (r < 1e-6)
 
 
+def test_mg_pcg_extension(oracle):
+    """MG-preconditioned CG (extension, parity unpinned): needs the symmetric cycle (full weighting); beats plain cycling."""
+    n = 129
+    b = np.asfortranarray(np.random.default_rng(1).random((n, n)))
+    for opt, plain in ((oracle.MGOpt(restriction=1), 8), (oracle.MGOpt(smoother=1, restriction=1), 5)):
+        x = oracle.farray((n, n))
+        r, it = oracle.mg_pcg2d(x, b, 1.0 / (n - 1), 0.0, 1e-6, 50, opt)
+        assert it < plain
+        lap = (x[2:, 1:-1] + x[:-2, 1:-1] + x[1:-1, 2:] + x[1:-1, :-2] - 4 * x[1:-1, 1:-1]) * (n - 1) ** 2
+        assert np.sqrt(np.sum((lap - b[1:-1, 1:-1]) ** 2) / (n * n)) < 2e-6 * np.sqrt(np.sum(b[1:-1, 1:-1] ** 2) / (n * n))
+    x = oracle.farray((n, n))
+    r, it = oracle.mg_pcg2d(x, b, 1.0 / (n - 1), 0.0, 1e-6, 30, oracle.MGOpt())  # injection: not symmetric -> stagnates
+    assert it == 30
+
+
 def test_error_conditions(oracle):
     x = oracle.farray((130, 130)); b = oracle.farray((130, 130)); b[:] = 1
     assert np.isnan(oracle.mgsolve2d(x, b, 1 / 129, 0.0, 1e-6, 5)[0])           # "ERROR:not a power of 2" multigrid.jl:96
