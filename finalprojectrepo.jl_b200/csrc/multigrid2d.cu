@@ -40,7 +40,8 @@ struct b2s_mg {
     double *u[kMaxLevels] = {}, *rhs[kMaxLevels] = {}, *tmp[kMaxLevels] = {};  // u/rhs for l >= 1, tmp for all
     int first_smem = 0;  // first level handled by the collapsed kernel
     size_t coarse_smem = 0;
-    MGCall *call_dev = nullptr, *call_pin = nullptr;
+    MGCall *call_dev = nullptr, *call_pin = nullptr;  // call_pin[0]: upload staging, call_pin[1]: download staging
+    double *hist_dev = nullptr, *hist_pin = nullptr;
     double *sumsq_dev = nullptr;  // [0] last sweep, [1] f, [2],[3] rbgs colours
     double *sumsq_pin = nullptr;
     int *sweeps_dev = nullptr;
@@ -132,10 +133,6 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
                     mg_rbgs_kernel<<<g, kMGBX, 0, st>>>(a);
                     ++n;
                 }
-            if (norm_on_last) {  // sumsq[0] = red + black
-                mg_axpy_kernel<<<1, 32, 0, st>>>(0.0, nullptr, h->sumsq_dev, 0, 3);
-                ++n;
-            }
         } else {
             for (int s = 0; s < 2; ++s) {
                 SweepArgs a = {};
@@ -263,6 +260,8 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
             ++n;
         }
     }
+    mg_cycle_end_kernel<<<1, 32, 0, st>>>(h->call_dev);  // r_rms, exit test, bookkeeping (multigrid.jl:64-75)
+    ++n;
     B2S_CUDA(cudaGetLastError());
     if (count) *count = n;
     return B2S_OK;
@@ -393,11 +392,18 @@ int launch_cycle(b2s_mg *h)
     return B2S_OK;
 }
 
-int set_call(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int apply_bcs, int bc_before)
+int set_call(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int apply_bcs, int bc_before,
+             int niters, int check)
 {
     MGCall &m = *h->call_pin;
     m.u = u; m.rhs = f; m.h = hgrid; m.c = c; m.tol = tol; m.apply_bcs = apply_bcs; m.bc_before = bc_before;
     m.sumsq = h->sumsq_dev; m.coarse_sweeps = h->sweeps_dev;
+    m.done = niters > 0 ? 0 : 1; m.ncycles = 0; m.niters = niters; m.check = check;
+    m.n_points = (double)h->nx[0] * h->ny[0];
+    m.hist = h->hist_dev;
+    const int fs = h->coarse_global ? h->nlev - 1 : h->first_smem;
+    m.rb_combine = (h->cfg.smoother == B2S_SMOOTH_RBGS && fs > 0) ? 1 : 0;
+    m.pad = 0;
     B2S_CUDA(cudaMemcpyAsync(h->call_dev, h->call_pin, sizeof(MGCall), cudaMemcpyHostToDevice, h->stream));
     return B2S_OK;
 }
@@ -415,6 +421,8 @@ int mg_destroy_impl(b2s_mg *h)
     }
     if (h->call_dev) cudaFree(h->call_dev);
     if (h->call_pin) cudaFreeHost(h->call_pin);
+    if (h->hist_dev) cudaFree(h->hist_dev);
+    if (h->hist_pin) cudaFreeHost(h->hist_pin);
     if (h->sumsq_dev) cudaFree(h->sumsq_dev);
     if (h->sumsq_pin) cudaFreeHost(h->sumsq_pin);
     if (h->sweeps_dev) cudaFree(h->sweeps_dev);
@@ -542,7 +550,9 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
             MG_CUDA(cudaMalloc(&h->cg_work, 4 * (size_t)h->nx[L - 1] * h->ny[L - 1] * sizeof(double)));
     }
     MG_CUDA(cudaMalloc(&h->call_dev, sizeof(MGCall)));
-    MG_CUDA(cudaMallocHost(&h->call_pin, sizeof(MGCall)));
+    MG_CUDA(cudaMallocHost(&h->call_pin, 2 * sizeof(MGCall)));
+    MG_CUDA(cudaMalloc(&h->hist_dev, kMaxHist * sizeof(double)));
+    MG_CUDA(cudaMallocHost(&h->hist_pin, kMaxHist * sizeof(double)));
     MG_CUDA(cudaMalloc(&h->sumsq_dev, 8 * sizeof(double)));
     MG_CUDA(cudaMemset(h->sumsq_dev, 0, 8 * sizeof(double)));
     MG_CUDA(cudaMallocHost(&h->sumsq_pin, 8 * sizeof(double)));
@@ -583,34 +593,53 @@ int b2s_mg_solve(b2s_mg *h, double *u, const double *f, double hgrid, double c, 
                  double *r_rms_out, int *ncycles, double *rel_hist)
 {
     B2S_REQUIRE(h && u && f, B2S_ERR_BAD_ARG, "NULL argument");
+    B2S_REQUIRE(niters <= kMaxHist, B2S_ERR_BAD_ARG, "niters %d exceeds %d", niters, kMaxHist);
     DeviceGuard guard;
     guard.set(h->cfg.device);
     const double N = (double)h->nx[0] * h->ny[0];
     B2S_CUDA(cudaEventRecord(h->ev0, h->stream));
-    B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs));
+    B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs, niters, 1));
     B2S_CHECK(enqueue_fnorm(h));  // f_rms = sqrt(sum(f.^2)/(nx*ny))   multigrid.jl:53
-    double r_rms = 0.0, f_rms = 0.0, tolf = 0.0;
-    int n = 0;
-    for (int iter = 1; iter <= niters; ++iter) {
-        B2S_CHECK(launch_cycle(h));
-        B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        B2S_CUDA(cudaStreamSynchronize(h->stream));  // @synchronize()   multigrid.jl:65
-        if (iter == 1) {
-            f_rms = sqrt(h->sumsq_pin[1] / N);
-            tolf = tol * f_rms;
+    // The loop "for iter = 1:niters ... break if r_rms < tolf" (multigrid.jl:58-76) runs on the device: the last kernel
+    // of every cycle evaluates the test and raises a flag that turns all later cycles into no-ops. The host enqueues
+    // cycles in batches sized from the observed contraction factor and polls one struct per batch.
+    MGCall *back = h->call_pin + 1;
+    back->done = niters > 0 ? 0 : 1;
+    back->ncycles = 0;
+    int launched = 0;
+    while (!back->done) {
+        int batch = 1;
+        if (!h->coarse_global) {
+            const int k = back->ncycles;
+            if (k < 2) batch = 2 - k;
+            else {  // predict the remaining cycles from the last contraction factor
+                const double a = h->hist_pin[k - 1], b = h->hist_pin[k - 2];
+                const double ratio = a / b;
+                batch = 1;
+                if (ratio > 0.0 && ratio < 0.9 && a > tol) batch = (int)ceil(log(tol / a) / log(ratio));
+                batch = std::max(1, std::min(batch, 8));
+            }
         }
-        r_rms = sqrt(h->sumsq_pin[0] / N);
-        n = iter;
-        if (rel_hist) rel_hist[iter - 1] = r_rms / f_rms;
-        if (r_rms < tolf) break;  // multigrid.jl:70-75
-        if (r_rms != r_rms) break;
+        batch = std::min(batch, niters - launched);
+        if (batch <= 0) batch = 1;
+        for (int i = 0; i < batch; ++i) B2S_CHECK(launch_cycle(h));
+        launched += batch;
+        B2S_CUDA(cudaMemcpyAsync(back, h->call_dev, sizeof(MGCall), cudaMemcpyDeviceToHost, h->stream));
+        B2S_CUDA(cudaMemcpyAsync(h->hist_pin, h->hist_dev, sizeof(double) * std::min(launched, kMaxHist), cudaMemcpyDeviceToHost,
+                                 h->stream));
+        B2S_CUDA(cudaStreamSynchronize(h->stream));  // @synchronize()   multigrid.jl:65
+        launched = back->ncycles;  // cycles enqueued after the exit were no-ops
     }
+    B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     B2S_CUDA(cudaEventRecord(h->ev1, h->stream));
     B2S_CUDA(cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     B2S_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
-    if (r_rms_out) *r_rms_out = r_rms;
+    const int n = back->ncycles;
+    if (rel_hist)
+        for (int i = 0; i < n; ++i) rel_hist[i] = h->hist_pin[i];
+    if (r_rms_out) *r_rms_out = n > 0 ? sqrt(h->sumsq_pin[0] / N) : 0.0;
     if (ncycles) *ncycles = n;
     return B2S_OK;
 }
@@ -620,7 +649,7 @@ int b2s_mg_vcycle(b2s_mg *h, double *u, const double *rhs, double hgrid, double 
     B2S_REQUIRE(h && u && rhs, B2S_ERR_BAD_ARG, "NULL argument");
     DeviceGuard guard;
     guard.set(h->cfg.device);
-    B2S_CHECK(set_call(h, u, rhs, hgrid, c, tol, apply_bcs, 0));
+    B2S_CHECK(set_call(h, u, rhs, hgrid, c, tol, apply_bcs, 0, 1, 0));
     B2S_CHECK(launch_cycle(h));
     B2S_CUDA(cudaMemcpyAsync(h->sumsq_pin, h->sumsq_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     B2S_CUDA(cudaStreamSynchronize(h->stream));
@@ -641,7 +670,7 @@ int b2s_mg_cycles(b2s_mg *h, double *u, const double *f, double hgrid, double c,
     B2S_REQUIRE(h && u && f && ncycles >= 0, B2S_ERR_BAD_ARG, "bad argument");
     DeviceGuard guard;
     guard.set(h->cfg.device);
-    B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs));
+    B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs, 1 << 30, 0));
     if (h->cfg.use_graph && !h->graph && ncycles > 0) {  // keep graph instantiation out of the timed region
         B2S_CHECK(launch_cycle(h));
         B2S_CUDA(cudaStreamSynchronize(h->stream));

@@ -27,7 +27,32 @@ struct MGCall {
     int bc_before;      // apply_boundary_conditions!(u) before the cycle (multigrid.jl:60-62)
     double *sumsq;      // [0]: sum res^2 of the last sweep on the finest level; [1]: sum f^2
     int *coarse_sweeps; // sweeps / iterations of the coarsest solve
+    // device-resident MGsolve loop (multigrid.jl:58-76): cycles enqueued after `done` is raised return at once
+    int done;           // every kernel of a cycle reads this together with the scalars above (same cache line)
+    int ncycles;        // V-cycles completed
+    int niters;         // cap
+    int check;          // 1: evaluate r_rms < tol*f_rms after every cycle (MGsolve); 0: fixed number of cycles
+    double n_points;    // nx*ny of the finest level
+    double *hist;       // r_rms / f_rms per cycle (capacity kMaxHist)
+    int rb_combine;     // 1: sumsq[0] = sumsq[2] + sumsq[3] (red + black) before the test
+    int pad;
 };
+constexpr int kMaxHist = 4096;
+
+// End of a V-cycle: r_rms, convergence test and bookkeeping on the device (multigrid.jl:64-75).
+__global__ void mg_cycle_end_kernel(MGCall *cp)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || cp->done) return;
+    double *ss = cp->sumsq;
+    if (cp->rb_combine) ss[0] = ss[2] + ss[3];
+    const double r_rms = sqrt(ss[0] / cp->n_points);
+    const double f_rms = sqrt(ss[1] / cp->n_points);
+    const int k = cp->ncycles;
+    if (k < kMaxHist) cp->hist[k] = r_rms / f_rms;
+    cp->ncycles = k + 1;
+    const double tolf = cp->tol * f_rms;
+    if ((cp->check && (r_rms < tolf || r_rms != r_rms)) || k + 1 >= cp->niters) cp->done = 1;
+}
 
 __device__ __forceinline__ double level_h(const MGCall *cp, int level)
 {
@@ -86,6 +111,7 @@ __global__ void __launch_bounds__(kMGBX) mg_sweep_kernel(const SweepArgs a)
 {
     __shared__ double red[32];
     if (a.loop != nullptr && a.loop->done) return;
+    if (a.cp != nullptr && a.cp->done) return;
     const double *u = a.u;
     const double *rhs = a.rhs;
     double *out = a.out;
@@ -152,6 +178,7 @@ struct RbgsArgs {
 __global__ void __launch_bounds__(kMGBX) mg_rbgs_kernel(const RbgsArgs a)
 {
     __shared__ double red[32];
+    if (a.cp != nullptr && a.cp->done) return;
     double *u = a.u;
     const double *rhs = a.rhs;
     double h = a.h, c = a.c;
@@ -223,6 +250,7 @@ __device__ __forceinline__ double coarse_value(const double *__restrict__ u, con
 
 __global__ void __launch_bounds__(256) mg_restrict_kernel(const RestrictArgs a)
 {
+    if (a.cp != nullptr && a.cp->done) return;
     const double *u = a.u;
     const double *rhs = a.rhs;
     double h = a.h, c = a.c;
@@ -285,6 +313,7 @@ struct ProlongArgs {
 
 __global__ void __launch_bounds__(kMGBX) mg_prolong_kernel(const ProlongArgs a)
 {
+    if (a.cp != nullptr && a.cp->done) return;
     double *fine = a.fine;
     int apply_bcs = a.apply_bcs;
     if (a.cp != nullptr) {
@@ -318,6 +347,7 @@ __global__ void __launch_bounds__(kMGBX) mg_prolong_smooth_kernel(const ProlongS
     const double *u = a.u;
     const double *rhs = a.rhs;
     const MGCall *cp = a.cp;
+    if (cp->done) return;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
     const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
@@ -423,6 +453,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     extern __shared__ __align__(16) double tsm[];
     double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
     const MGCall *cp = a.cp;
+    if (cp->done) return;
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
@@ -510,6 +541,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     __shared__ double red[32];
     double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows, *Cw = tsm + 3 * kTP * kTRows;
     const MGCall *cp = a.cp;
+    if (cp->done) return;
     const double *rhs = a.rhs;
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
@@ -596,6 +628,7 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
 {
     __shared__ double U0[kSRing][kSP], Fr[kSRing][kSP], S1[4][kSP], S2[4][kSP];
     const MGCall *cp = a.cp;
+    if (cp->done) return;
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
@@ -692,6 +725,7 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
     __shared__ double Us[kSRing][kSP], Fr[kSRing][kSP], C0[4][kSP], T1[4][kSP], Ec[kSCRing][kSCP];
     __shared__ double red[32];
     const MGCall *cp = a.cp;
+    if (cp->done) return;
     const double *rhs = a.rhs;
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
@@ -809,7 +843,7 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
 __global__ void mg_bc_kernel(const MGCall *cp, double *T, int nx, int ny, int kind)
 {
     if (cp != nullptr) {
-        if (!cp->bc_before) return;
+        if (cp->done || !cp->bc_before) return;
         T = cp->u;
     }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1193,6 +1227,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
     extern __shared__ double sm[];
     __shared__ double red[32];
     const MGCall *cp = a.cp;
+    if (cp->done) return;
     const double c = cp->c, tol = cp->tol;
     const int apply_bcs = cp->apply_bcs;
     const bool fw = a.restriction == B2S_RESTRICT_FW;

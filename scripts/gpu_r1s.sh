@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_multigrid.py -m gpu -q -k "pcg or large_coarsest or cg_larger" > gpurun_out/r1s_pytest_mg.log 2>&1
+echo "pytest exit $?" >> gpurun_out/r1s_pytest_mg.log

@@ -207,6 +207,38 @@ def test_cg_larger_than_shared_memory(p2, oracle):
     assert np.max(np.abs(p2.to_host(x) - xo)) <= 1e-8 * np.max(np.abs(xo))
 
 
+@pytest.mark.parametrize("shape,cs", [((5, 5), 5), ((9, 9), 5), ((17, 5), 5), ((17, 17), 9), ((33, 33), 5), ((65, 65), 5),
+                                      ((65, 17), 5), ((129, 33), 9)])
+@pytest.mark.parametrize("bcs", [False, True])
+def test_small_grids_whole_hierarchy_in_shared_memory(p2, oracle, shape, cs, bcs):
+    """Tiny problems: the finest level itself lives in the collapsed kernel (or is the coarsest level); the caller's u is
+    the initial guess there. Ragged / non-square shapes, with and without the BC handling."""
+    nx, ny = shape
+    h = 1.0 / (min(nx, ny) - 1)
+    u0, f = rnd(shape, 41), rnd(shape, 42)
+    uo = u0.copy(order="F")
+    r_o, nc_o, hist_o = oracle.mgsolve2d(uo, f, h, 2.5, 1e-8, 12, apply_BCs=bcs, opt=oracle.MGOpt(coarse_solve_size=cs))
+    du = p2.to_device(u0)
+    hd = p2.preallocate_buffers(nx, ny, p2.MGOpt(coarse_solve_size=cs))
+    r_g, nc_g, hist_g = hd.solve(du, p2.to_device(f), h, 2.5, 1e-8, 12, bcs, want_hist=True)
+    assert nc_g == nc_o
+    assert np.allclose(hist_g, hist_o, rtol=1e-9, atol=0)
+    assert np.array_equal(p2.to_host(du), uo)
+    hd.close()
+
+
+def test_zero_iterations_and_zero_rhs(p2):
+    n = 129
+    x = p2.to_device(rnd((n, n), 5))
+    x0 = p2.to_host(x)
+    hd = p2.preallocate_buffers(n, n)
+    r, nc = hd.solve(x, p2.zeros(n, n), 1.0 / (n - 1), 0.0, 1e-6, 0, False)   # for iter = 1:0 never runs -> r_rms = 0.0
+    assert (r, nc) == (0.0, 0) and np.array_equal(p2.to_host(x), x0)
+    r, nc = hd.solve(x, p2.zeros(n, n), 1.0 / (n - 1), 0.0, 1e-6, 3, False)   # f = 0: tolf = 0, "r < 0" never true
+    assert nc == 3 and r >= 0.0
+    hd.close()
+
+
 def test_variant_b_five_cycles(p2, oracle):
     n = 1025
     b = rnd((n, n), 1)
