@@ -173,7 +173,30 @@ def mg_bench(device, peak):
         out["navier_stokes_2049"] = part2.bench_navier_stokes(device=device)
     except Exception as e:  # pragma: no cover
         out["navier_stokes_2049"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    try:
+        out["cpu_baseline_1025"] = mg_cpu_baseline(1025)
+    except Exception as e:  # pragma: no cover
+        out["cpu_baseline_1025"] = {"unavailable": f"{type(e).__name__}: {e}"}
     return out
+
+
+def mg_cpu_baseline(n):
+    """The reference's CPU (Threads) multigrid path -- the OpenMP oracle port with the reference's un-fused passes -- on the
+    same bench shape (multigrid_bench.jl: x = 0, b ~ U[0,1), tol 1e-6), timed on the host cores of this box."""
+    import numpy as np
+    from oracle import oracle_lib as O
+    O.build()
+    b = np.asfortranarray(np.random.default_rng(1).random((n, n)))
+    opt = O.MGOpt(unfused=1)
+    x = O.farray((n, n))
+    O.mgsolve2d(x, b, 1.0 / (n - 1), 0.0, 1e-6, 100, opt=opt)  # warm-up
+    x = O.farray((n, n))
+    t0 = time.perf_counter()
+    r, nc, _ = O.mgsolve2d(x, b, 1.0 / (n - 1), 0.0, 1e-6, 100, opt=opt)
+    dt = time.perf_counter() - t0
+    return {"kind": "port", "cores": O.num_threads(), "grid": [n, n], "vcycles": nc, "solve_ms": dt * 1e3,
+            "ms_per_vcycle": dt / nc * 1e3, "dof_per_s_per_vcycle": n * n * nc / dt,
+            "sample": f"one full MG solve ({nc} V-cycles) of the {n}^2 bench shape, OpenMP oracle port, un-fused passes"}
 
 
 def main():

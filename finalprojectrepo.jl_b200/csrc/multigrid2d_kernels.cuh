@@ -645,6 +645,12 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
     }
     const int s_begin = Y0 - 3, s_end = Y1 + 2;
     const double *gu = u + (dx ? x : 0), *gf = rhs + (dx ? x : 0);
+    // per-column facts of the coarse point (x/2, .) this thread writes on even rows
+    const bool xeven = (x & 1) == 0;
+    const int Ic = x >> 1;
+    const bool cint = Ic >= 1 && Ic <= nxc - 2;
+    const bool cmir_lo = apply_bcs && Ic == 1, cmir_hi = apply_bcs && Ic == nxc - 2;
+    const bool cedge_bc = apply_bcs && (Ic == 0 || Ic == nxc - 1);
 #pragma unroll
     for (int j = 0; j < kSD; ++j) {  // prologue: rows s_begin .. s_begin+kSD-1 -> slots 0 .. kSD-1
         const int r = s_begin + j;
@@ -677,7 +683,7 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
             // stage A: first sweep at row s-1
             const int ya = s - 1;
             double p_c = u_b;
-            if (ix && ya >= 1 && ya <= ny - 2) {
+            if (ix && (unsigned)(ya - 1) < (unsigned)(ny - 2)) {
                 const double *row = U0[(j + kSRing - 1) % kSRing];
                 const double res = ((row[c + 1] + row[c - 1] + u_c + u_a - k.C * u_b) * k._h2 - f_c);
                 p_c = u_b + k.w * res;
@@ -686,7 +692,7 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
             // stage B: second sweep at row s-2 (x neighbours of S1[s-2] were published one step ago)
             const int yb = s - 2;
             double q_c = p_b;
-            if (ix && yb >= 1 && yb <= ny - 2) {
+            if (ix && (unsigned)(yb - 1) < (unsigned)(ny - 2)) {
                 const double *row = S1[(j + 2) & 3];
                 const double res = ((row[c + 1] + row[c - 1] + p_c + p_a - k.C * p_b) * k._h2 - f_b);
                 q_c = p_b + k.w * res;
@@ -694,22 +700,21 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
             S2[(j + 2) & 3][c] = q_c;
             // stage C: output row s-3: smoothed u, injected residual -> coarse rhs, coarse unknown = 0
             const int yc = s - 3;
-            if (yc >= Y0 && yc < Y1 && outcol) {
+            if (outcol && (unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
                 a.u_out[(size_t)x + (size_t)nx * yc] = q_b;
-                if (((x | yc) & 1) == 0) {
-                    const int I = x >> 1, J = yc >> 1;
-                    const size_t pc = (size_t)I + (size_t)nxc * J;
+                // yc = Y0 - 6 + (s0 - s_begin) + j with Y0, kSRing even: the row is even iff j is even (compile time)
+                if ((j & 1) == 0 && xeven) {
+                    const int J = yc >> 1;
+                    const size_t pc = (size_t)Ic + (size_t)nxc * J;
                     a.ec[pc] = 0.0;
-                    const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
-                    if (interior) {
+                    const bool jint = (unsigned)(J - 1) < (unsigned)(nyc - 2);
+                    if (cint && jint) {
                         const double *row = S2[(j + 1) & 3];
                         const double v = ((row[c + 1] + row[c - 1] + q_c + q_a - k.C * q_b) * k._h2 - f_a);
                         a.rc[pc] = v;
-                        if (apply_bcs) {
-                            if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
-                            if (I == nxc - 2) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
-                        }
-                    } else if (!(apply_bcs && (I == 0 || I == nxc - 1) && J >= 1 && J <= nyc - 2)) {
+                        if (cmir_lo) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                        if (cmir_hi) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+                    } else if (!(cedge_bc && jint)) {
                         a.rc[pc] = 0.0;
                     }
                 }
@@ -807,7 +812,7 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
             // stage B: first post-sweep at row s-1
             const int yb = s - 1;
             double t_c = c_b;
-            if (ix && yb >= 1 && yb <= ny - 2) {
+            if (ix && (unsigned)(yb - 1) < (unsigned)(ny - 2)) {
                 const double *row = C0[(j + 3) & 3];
                 const double res = ((row[c + 1] + row[c - 1] + c_c + c_a - k.C * c_b) * k._h2 - f_b);
                 t_c = c_b + k.w * res;
@@ -815,9 +820,9 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
             T1[(j + 3) & 3][c] = t_c;
             // stage C: second post-sweep at row s-2 -> u, sum of its pre-update res^2
             const int yc = s - 2;
-            if (yc >= Y0 && yc < Y1 && outcol) {
+            if (outcol && (unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
                 double v = t_b;
-                if (ix && yc >= 1 && yc <= ny - 2) {
+                if (ix && (unsigned)(yc - 1) < (unsigned)(ny - 2)) {
                     const double *row = T1[(j + 2) & 3];
                     const double res = ((row[c + 1] + row[c - 1] + t_c + t_a - k.C * t_b) * k._h2 - f_a);
                     acc += res * res;
