@@ -163,12 +163,25 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     // 2 = tiles everywhere, 3 = streaming everywhere
     auto use_streaming = [&](int l) {
         if (c.fuse_sweeps == 2) return false;
-        if (c.fuse_sweeps == 3) return true;
+        if (c.fuse_sweeps == 3 || c.fuse_sweeps == 4) return true;
         return (size_t)h->nx[l] * h->ny[l] > (size_t)1500000;
     };
+    const bool two_col = c.fuse_sweeps != 3;  // 1 (auto) and 4: two columns per thread; 3: one column per thread
+    auto stream2_rows = [&](int l) {
+        const int bx = (h->nx[l] + kS2W - 1) / kS2W, ny = h->ny[l], slots = 148 * 4;
+        int ch = 16;
+        for (int w = 1; w <= 64; ++w) {
+            const int chunks = std::max(1, (w * slots) / bx);
+            ch = (ny + chunks - 1) / chunks;
+            if (ch <= 256) break;
+        }
+        if (h->stream_ch > 0) ch = h->stream_ch;
+        return std::max(16, (ch + 1) & ~1);
+    };
+    auto stream2_grid = [&](int l, int ch) { return dim3((h->nx[l] + kS2W - 1) / kS2W, (h->ny[l] + ch - 1) / ch, 1); };
     auto stream_rows = [&](int l) {
         // rows per chunk (even, >= 16, <= ~256): the grid should fill whole waves of 148 SMs x 6 resident blocks
-        const int bx = (h->nx[l] + kSW - 1) / kSW, ny = h->ny[l], slots = 148 * 6;
+        const int bx = (h->nx[l] + kSW - 1) / kSW, ny = h->ny[l], slots = 148 * B2S_STREAM_MINBLOCKS;
         int ch = 16;
         for (int w = 1; w <= 64; ++w) {
             const int chunks = std::max(1, (w * slots) / bx);
@@ -183,7 +196,10 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = 0; l < fs && fused; ++l) {
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
-        if (use_streaming(l)) {
+        if (use_streaming(l) && two_col) {
+            const int ch = stream2_rows(l);
+            mg_down_stream2_kernel<<<stream2_grid(l, ch), kS2NT, kS2SmemDown, st>>>(t, ch);
+        } else if (use_streaming(l)) {
             const int ch = stream_rows(l);
             mg_down_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
         } else {
@@ -226,7 +242,10 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        if (use_streaming(l)) {
+        if (use_streaming(l) && two_col) {
+            const int ch = stream2_rows(l);
+            mg_up_stream2_kernel<<<stream2_grid(l, ch), kS2NT, kS2SmemUp, st>>>(t, ch);
+        } else if (use_streaming(l)) {
             const int ch = stream_rows(l);
             mg_up_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
         } else {
@@ -567,6 +586,8 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         h->tile_choice = (e && *e) ? atoi(e) : 0;
         if (h->tile_choice < 0 || h->tile_choice > 3) h->tile_choice = 0;
         MG_CUDA(tile_set_attr(h->tile_choice));
+        MG_CUDA(cudaFuncSetAttribute(mg_down_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemDown));
+        MG_CUDA(cudaFuncSetAttribute(mg_up_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemUp));
         const char *e2 = getenv("B2S_MG_CH");
         h->stream_ch = (e2 && *e2) ? atoi(e2) : 0;
         const char *e3 = getenv("B2S_MG_PROF");

@@ -615,18 +615,68 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSNT = 128;         // threads per block = strip columns including the halo
 constexpr int kSW = kSNT - 6;     // output columns per strip (even)
-constexpr int kSD = 6;            // prefetch depth in rows
-constexpr int kSRing = 12;        // ring rows for the streamed inputs (> kSD + 2, a multiple of 4; = unroll factor)
+#ifndef B2S_STREAM_D
+#define B2S_STREAM_D 6
+#define B2S_STREAM_RING 12
+#define B2S_STREAM_MINBLOCKS 6
+#endif
+constexpr int kSD = B2S_STREAM_D;        // prefetch depth in rows
+constexpr int kSRing = B2S_STREAM_RING;  // ring rows for the streamed inputs (> kSD + 2, a multiple of 4; = unroll factor)
 constexpr int kSCRing = kSRing / 2;  // coarse-row ring of the upward kernel
 constexpr int kSP = kSNT + 2;     // ring row pitch: one pad element on each side
 constexpr int kSCW = kSW / 2 + 5; // coarse window width of the upward kernel
 constexpr int kSCP = kSCW + 1;
 
+constexpr int kSP2 = kSNT + 4;    // pitch of the bulk-copied input rings (parity shift + pads, rows stay 16-byte aligned)
+
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One elected thread streams row r of two fields (the strip's columns X0-3 .. X0+kSNT-4, clipped to the grid) into ring
+// rows with 1-D bulk copies (UBLKCP): no per-thread address arithmetic and no LSU traffic for the loads. Rows of a
+// (2^k+1)-wide grid start at alternating 8-byte parities, bulk copies need 16-byte alignment on both sides: the copy
+// starts at the even element at or before the first needed one and lands in the ring row shifted by the row parity
+// (column x of row r sits at index x-(X0-4)+(r&1)); the consumers know that parity at compile time.
+__device__ __forceinline__ void stream_issue_row(double *ringA, double *ringB, const double *gA, const double *gB, int r, int slot,
+                                                 uint64_t *bar, int X0, int nx, int ny, int r_last)
+{
+    if (r < 0 || r >= ny || r > r_last) { mbar_arrive_plain(bar); return; }
+    const int x_lo = max(X0 - 3, 0), x_hi = min(X0 + kSNT - 4, nx - 1);
+    long long g0 = (long long)x_lo + (long long)nx * r;
+    const int shift = (int)(g0 & 1);
+    g0 -= shift;
+    int n_el = ((x_hi - x_lo + 1) + shift + 1) & ~1;
+    const long long total = (long long)nx * ny;
+    const int dst = (x_lo - shift) - (X0 - 4) + (r & 1);
+    double *dA = ringA + (size_t)slot * kSP2 + dst, *dB = ringB + (size_t)slot * kSP2 + dst;
+    if (g0 + n_el > total) {  // the last pair would read one element past the array: fetch the last element by hand
+        n_el -= 2;
+        dA[n_el] = gA[total - 1];
+        dB[n_el] = gB[total - 1];
+    }
+    if (n_el <= 0) { mbar_arrive_plain(bar); return; }
+    const uint32_t bytes = (uint32_t)n_el * 8u;
+    mbar_arrive_expect_tx(bar, 2u * bytes);
+    bulk_copy_g2s(dA, gA + g0, bytes, bar);
+    bulk_copy_g2s(dB, gB + g0, bytes, bar);
+}
+
 // Ring slots are relative to the first streamed row of the block, and the row loop is unrolled by the ring size, so
 // every shared-memory index below is a compile-time constant and the register queues rotate by renaming.
-__global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, int ch)
+__global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_down_stream_kernel(const TileArgs a, int ch)
 {
-    __shared__ double U0[kSRing][kSP], Fr[kSRing][kSP], S1[4][kSP], S2[4][kSP];
+    __shared__ __align__(128) double U0[kSRing][kSP2], Fr[kSRing][kSP2];
+    __shared__ double S1[4][kSP], S2[4][kSP];
+    __shared__ uint64_t bars[kSRing];
     const MGCall *cp = a.cp;
     if (cp->done) return;
     const double *u = a.u_in, *rhs = a.rhs;
@@ -639,52 +689,48 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
     const int x = X0 - 3 + t;
     const bool dx = x >= 0 && x < nx, ix = x >= 1 && x <= nx - 2;
     const bool outcol = t >= 3 && t <= kSNT - 4 && dx;
-    if (t == 0) {  // pads are read by the (unused) edge columns only; keep them finite
-        for (int r = 0; r < kSRing; ++r) { U0[r][0] = 0.0; U0[r][kSP - 1] = 0.0; }
-        for (int r = 0; r < 4; ++r) { S1[r][0] = 0.0; S1[r][kSP - 1] = 0.0; S2[r][0] = 0.0; S2[r][kSP - 1] = 0.0; }
-    }
     const int s_begin = Y0 - 3, s_end = Y1 + 2;
-    const double *gu = u + (dx ? x : 0), *gf = rhs + (dx ? x : 0);
+    if (t == 0) {
+        for (int r = 0; r < 4; ++r) { S1[r][0] = 0.0; S1[r][kSP - 1] = 0.0; S2[r][0] = 0.0; S2[r][kSP - 1] = 0.0; }
+        for (int r = 0; r < kSRing; ++r) mbar_init(&bars[r], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int j = 0; j < kSD; ++j)  // prologue: rows s_begin .. s_begin+kSD-1 -> slots 0 .. kSD-1
+            stream_issue_row(&U0[0][0], &Fr[0][0], u, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
+    }
+    __syncthreads();
     // per-column facts of the coarse point (x/2, .) this thread writes on even rows
     const bool xeven = (x & 1) == 0;
     const int Ic = x >> 1;
     const bool cint = Ic >= 1 && Ic <= nxc - 2;
     const bool cmir_lo = apply_bcs && Ic == 1, cmir_hi = apply_bcs && Ic == nxc - 2;
     const bool cedge_bc = apply_bcs && (Ic == 0 || Ic == nxc - 1);
-#pragma unroll
-    for (int j = 0; j < kSD; ++j) {  // prologue: rows s_begin .. s_begin+kSD-1 -> slots 0 .. kSD-1
-        const int r = s_begin + j;
-        const bool in = dx && r >= 0 && r < ny;
-        const size_t off = in ? (size_t)nx * r : 0;
-        cp_async8(&U0[j][c], gu + off, in);
-        cp_async8(&Fr[j][c], gf + off, in);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
     double u_a = 0.0, u_b = 0.0, u_c = 0.0;  // U0 rows s-2, s-1, s of this column
     double p_a = 0.0, p_b = 0.0;             // S1 rows s-3, s-2
     double q_a = 0.0, q_b = 0.0;             // S2 rows s-4, s-3
     double f_a = 0.0, f_b = 0.0, f_c = 0.0, f_d = 0.0;  // rhs rows s-3 .. s
-    for (int s0 = s_begin; s0 <= s_end; s0 += kSRing) {
+    uint32_t phase = 0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kSRing, phase ^= 1u) {
 #pragma unroll
         for (int j = 0; j < kSRing; ++j) {
             const int s = s0 + j;
-            {
-                const int r = s + kSD;
-                const bool in = dx && r >= 0 && r < ny && r <= s_end;
-                const size_t off = in ? (size_t)nx * r : 0;
-                cp_async8(&U0[(j + kSD) % kSRing][c], gu + off, in);
-                cp_async8(&Fr[(j + kSD) % kSRing][c], gf + off, in);
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
-            asm volatile("cp.async.wait_group %0;" ::"n"(kSD) : "memory");
-            __syncthreads();
-            u_a = u_b; u_b = u_c; u_c = U0[j][c];
-            f_a = f_b; f_b = f_c; f_c = f_d; f_d = Fr[j][c];
+            // row s sits in slot j, shifted by its parity: s = Y0 - 3 + (multiple of kSRing) + j with Y0, kSRing even
+            constexpr int kDummy = 0; (void)kDummy;
+            const int sg = (j + 1) & 1;       // parity shift of row s
+            const int sg_a = j & 1;           // ... of row s-1
+            mbar_wait(&bars[j], phase);
+            __syncthreads();                   // publishes the S1/S2 rows of the previous step; all reads of slot j+kSD done
+            if (t == 0)
+                stream_issue_row(&U0[0][0], &Fr[0][0], u, rhs, s + kSD, (j + kSD) % kSRing, &bars[(j + kSD) % kSRing], X0, nx, ny,
+                                 s_end);
+            u_a = u_b; u_b = u_c; u_c = U0[j][c + sg];
+            f_a = f_b; f_b = f_c; f_c = f_d; f_d = Fr[j][c + sg];
             // stage A: first sweep at row s-1
             const int ya = s - 1;
             double p_c = u_b;
             if (ix && (unsigned)(ya - 1) < (unsigned)(ny - 2)) {
-                const double *row = U0[(j + kSRing - 1) % kSRing];
+                const double *row = U0[(j + kSRing - 1) % kSRing] + sg_a;
                 const double res = ((row[c + 1] + row[c - 1] + u_c + u_a - k.C * u_b) * k._h2 - f_c);
                 p_c = u_b + k.w * res;
             }
@@ -725,9 +771,11 @@ __global__ void __launch_bounds__(kSNT) mg_down_stream_kernel(const TileArgs a, 
     }
 }
 
-__global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, int ch)
+__global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_up_stream_kernel(const TileArgs a, int ch)
 {
-    __shared__ double Us[kSRing][kSP], Fr[kSRing][kSP], C0[4][kSP], T1[4][kSP], Ec[kSCRing][kSCP];
+    __shared__ __align__(128) double Us[kSRing][kSP2], Fr[kSRing][kSP2];
+    __shared__ double C0[4][kSP], T1[4][kSP], Ec[kSCRing][kSCP];
+    __shared__ uint64_t bars[kSRing];
     __shared__ double red[32];
     const MGCall *cp = a.cp;
     if (cp->done) return;
@@ -756,7 +804,6 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
     const bool xodd = xs & 1;
     const int s_begin = Y0 - 2, s_end = Y1 + 1;  // s_begin is even: row parity == slot parity
     const int K0 = s_begin >> 1;                  // coarse row held by slot 0 of the coarse ring
-    const double *gu = a.u_in + (dx ? x : 0), *gf = rhs + (dx ? x : 0);
     const int Ic = cx0 + t;
     const bool cin = t < kSCW && Ic >= 1 && Ic <= nxc - 2;
     const double *gc = a.ec + (cin ? Ic : 0);
@@ -768,38 +815,41 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
             cp_async8(&Ec[slot][t], gc + (in ? (size_t)nxc * K : 0), in);
         }
     };
+    if (t == 0) {
+        for (int r = 0; r < kSRing; ++r) mbar_init(&bars[r], 1);
+        fence_mbar_init();
+        fence_proxy_async();
 #pragma unroll
-    for (int j = 0; j < kSD; ++j) {
-        const int r = s_begin + j;
-        const bool in = dx && r >= 0 && r < ny;
-        const size_t off = in ? (size_t)nx * r : 0;
-        cp_async8(&Us[j][c], gu + off, in);
-        cp_async8(&Fr[j][c], gf + off, in);
+        for (int j = 0; j < kSD; ++j)
+            stream_issue_row(&Us[0][0], &Fr[0][0], a.u_in, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
+    }
+#pragma unroll
+    for (int j = 0; j < kSD; ++j) {  // the (quarter-size) coarse rows keep using per-thread cp.async
         if (j == 0) issue_coarse(0, 0);
         if (j & 1) issue_coarse((j + 1) >> 1, ((j + 1) >> 1) % kSCRing);  // coarse row K is first needed by fine row 2K-1
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    __syncthreads();
     double c_a = 0.0, c_b = 0.0;  // corrected u rows s-2, s-1
     double t_a = 0.0, t_b = 0.0;  // first-sweep rows s-3, s-2
     double f_a = 0.0, f_b = 0.0, f_c = 0.0;  // rhs rows s-2 .. s
     double acc = 0.0;
-    for (int s0 = s_begin; s0 <= s_end; s0 += kSRing) {
+    uint32_t phase = 0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kSRing, phase ^= 1u) {
         const int m0 = (s0 - s_begin) >> 1;
 #pragma unroll
         for (int j = 0; j < kSRing; ++j) {
             const int s = s0 + j;
-            {
-                const int r = s + kSD;
-                const bool in = dx && r >= 0 && r < ny && r <= s_end;
-                const size_t off = in ? (size_t)nx * r : 0;
-                cp_async8(&Us[(j + kSD) % kSRing][c], gu + off, in);
-                cp_async8(&Fr[(j + kSD) % kSRing][c], gf + off, in);
-                if ((j + kSD) & 1) issue_coarse(m0 + ((j + kSD + 1) >> 1), ((j + kSD + 1) >> 1) % kSCRing);
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
+            const int sg = j & 1;  // parity shift of row s (s_begin, kSRing even)
+            if ((j + kSD) & 1) issue_coarse(m0 + ((j + kSD + 1) >> 1), ((j + kSD + 1) >> 1) % kSCRing);
+            asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kSD) : "memory");
+            mbar_wait(&bars[j], phase);
             __syncthreads();
-            f_a = f_b; f_b = f_c; f_c = Fr[j][c];
+            if (t == 0)
+                stream_issue_row(&Us[0][0], &Fr[0][0], a.u_in, rhs, s + kSD, (j + kSD) % kSRing, &bars[(j + kSD) % kSRing], X0, nx,
+                                 ny, s_end);
+            f_a = f_b; f_b = f_c; f_c = Fr[j][c + sg];
             // stage A: corrected u at row s:  u_s - P(ec)
             double e;
             {
@@ -807,7 +857,7 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
                 if (!(j & 1)) e = xodd ? 0.5 * r0[0] + 0.5 * r0[1] : r0[0];
                 else e = xodd ? ((0.25 * r0[0] + 0.25 * r0[1]) + 0.25 * r1[0]) + 0.25 * r1[1] : 0.5 * r0[0] + 0.5 * r1[0];
             }
-            const double c_c = Us[j][c] - e;
+            const double c_c = Us[j][c + sg] - e;
             C0[j & 3][c] = c_c;
             // stage B: first post-sweep at row s-1
             const int yb = s - 1;
@@ -829,6 +879,310 @@ __global__ void __launch_bounds__(kSNT) mg_up_stream_kernel(const TileArgs a, in
                     v = t_b + k.w * res;
                 }
                 out[(size_t)x + (size_t)nx * yc] = v;
+            }
+            c_a = c_b; c_b = c_c;
+            t_a = t_b; t_b = t_c;
+        }
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-columns-per-thread streaming kernels: same pipeline as above, but every thread owns two adjacent columns, so one
+// of the two x neighbours of each point is a register of the same thread, own-column values are read and stage results
+// published as 16-byte pairs, the per-row index/predicate overhead is shared by two points, and a thread carries twice
+// as many independent FP64 dependency chains (the chains, not issue slots or HBM, bound the one-column version:
+// profiles/r01_ncu_source_mg_down_stream.md). Strip = 256 columns (248 outputs + 4 halo columns per side).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kS2NT = 128;
+constexpr int kS2W = 2 * kS2NT - 8;   // output columns per strip
+constexpr int kS2D = 6, kS2Ring = 8;  // bulk-copy prefetch depth (<= ring - 2) / ring rows (= unroll factor, multiple of 4)
+constexpr int kS2DC = 4;              // look-ahead of the coarse rows (cp.async groups), <= 2 * kS2CRing - 4
+constexpr int kS2CRing = kS2Ring / 2;
+constexpr int kS2P = 2 * kS2NT + 4;   // ring pitch: 2 pad elements left, parity shift, right pad (even)
+constexpr int kS2CW = kS2NT + 2;      // coarse window width
+constexpr int kS2CP = kS2CW + 2;
+constexpr size_t kS2SmemDown = ((size_t)2 * kS2Ring * kS2P + (size_t)2 * 4 * kS2P) * sizeof(double) + kS2Ring * sizeof(uint64_t);
+constexpr size_t kS2SmemUp = kS2SmemDown + (size_t)kS2CRing * kS2CP * sizeof(double);
+
+// bulk-copy one row of two fields for a 256-column strip starting at column X0-4 (see stream_issue_row)
+__device__ __forceinline__ void stream2_issue_row(double *ringA, double *ringB, const double *gA, const double *gB, int r, int slot,
+                                                  uint64_t *bar, int X0, int nx, int ny, int r_last)
+{
+    if (r < 0 || r >= ny || r > r_last) { mbar_arrive_plain(bar); return; }
+    const int x_lo = max(X0 - 4, 0), x_hi = min(X0 + 2 * kS2NT - 5, nx - 1);
+    long long g0 = (long long)x_lo + (long long)nx * r;
+    const int shift = (int)(g0 & 1);
+    g0 -= shift;
+    int n_el = ((x_hi - x_lo + 1) + shift + 1) & ~1;
+    const long long total = (long long)nx * ny;
+    const int dst = (x_lo - shift) - (X0 - 4) + 2 + (r & 1);
+    double *dA = ringA + (size_t)slot * kS2P + dst, *dB = ringB + (size_t)slot * kS2P + dst;
+    if (g0 + n_el > total) {
+        n_el -= 2;
+        dA[n_el] = gA[total - 1];
+        dB[n_el] = gB[total - 1];
+    }
+    if (n_el <= 0) { mbar_arrive_plain(bar); return; }
+    const uint32_t bytes = (uint32_t)n_el * 8u;
+    mbar_arrive_expect_tx(bar, 2u * bytes);
+    bulk_copy_g2s(dA, gA + g0, bytes, bar);
+    bulk_copy_g2s(dB, gB + g0, bytes, bar);
+}
+
+// own pair of a ring row (columns x0, x0+1 at indices ci+SG, ci+SG+1): one 16-byte load when the row's parity shift SG
+// keeps it aligned, two 8-byte loads otherwise
+template <int SG>
+__device__ __forceinline__ double2 ld_pair(const double *row, int ci)
+{
+    if (SG == 0) return *reinterpret_cast<const double2 *>(row + ci);
+    return make_double2(row[ci + 1], row[ci + 2]);
+}
+
+__device__ __forceinline__ double jac_res(double xp, double xm, double yp, double ym, double c, double f, const Coef &k)
+{
+    return ((xp + xm + yp + ym - k.C * c) * k._h2 - f);
+}
+
+__global__ void __launch_bounds__(kS2NT) mg_down_stream2_kernel(const TileArgs a, int ch)
+{
+    extern __shared__ __align__(128) unsigned char s2raw[];
+    double *U0 = reinterpret_cast<double *>(s2raw);       // [kS2Ring][kS2P]
+    double *Fr = U0 + kS2Ring * kS2P;                     // [kS2Ring][kS2P]
+    double *S1 = Fr + kS2Ring * kS2P;                     // [4][kS2P]
+    double *S2 = S1 + 4 * kS2P;                           // [4][kS2P]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(S2 + 4 * kS2P);
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double *u = a.u_in, *rhs = a.rhs;
+    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int t = threadIdx.x, ci = 2 * t + 2;  // index of the thread's first column in a ring row (before the shift)
+    const int X0 = blockIdx.x * kS2W, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);
+    const int x0 = X0 - 4 + 2 * t, x1 = x0 + 1;
+    const bool d0 = x0 >= 0 && x0 < nx, d1 = x1 >= 0 && x1 < nx;
+    const bool i0 = x0 >= 1 && x0 <= nx - 2, i1 = x1 >= 1 && x1 <= nx - 2;
+    const bool outt = t >= 2 && t <= kS2NT - 3;
+    const bool o0 = outt && d0, o1 = outt && d1;
+    const int s_begin = Y0 - 3, s_end = Y1 + 2;
+    if (t == 0) {
+        for (int r = 0; r < 4; ++r) {
+            S1[r * kS2P + 0] = S1[r * kS2P + 1] = S1[r * kS2P + kS2P - 2] = S1[r * kS2P + kS2P - 1] = 0.0;
+            S2[r * kS2P + 0] = S2[r * kS2P + 1] = S2[r * kS2P + kS2P - 2] = S2[r * kS2P + kS2P - 1] = 0.0;
+        }
+        for (int r = 0; r < kS2Ring; ++r) mbar_init(&bars[r], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int j = 0; j < kS2D; ++j) stream2_issue_row(U0, Fr, u, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
+    }
+    __syncthreads();
+    const int Ic = x0 >> 1;  // x0 is even: the coarse column this thread writes on even rows
+    const bool cint = Ic >= 1 && Ic <= nxc - 2;
+    const bool cmir_lo = apply_bcs && Ic == 1, cmir_hi = apply_bcs && Ic == nxc - 2;
+    const bool cedge_bc = apply_bcs && (Ic == 0 || Ic == nxc - 1);
+    double2 u_a = make_double2(0.0, 0.0), u_b = u_a, u_c = u_a;  // U0 rows s-2, s-1, s
+    double2 p_a = u_a, p_b = u_a, q_a = u_a, q_b = u_a;          // S1 rows s-3, s-2 ; S2 rows s-4, s-3
+    double2 f_a = u_a, f_b = u_a, f_c = u_a, f_d = u_a;          // rhs rows s-3 .. s
+    uint32_t phase = 0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kS2Ring, phase ^= 1u) {
+#pragma unroll
+        for (int j = 0; j < kS2Ring; ++j) {
+            const int s = s0 + j;
+            constexpr int kOdd = 1;
+            const int sg = (j + kOdd) & 1;  // parity shift of row s (= Y0 - 3 + multiple of kS2Ring + j), of row s-1: j & 1
+            mbar_wait(&bars[j], phase);
+            __syncthreads();
+            if (t == 0)
+                stream2_issue_row(U0, Fr, u, rhs, s + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny, s_end);
+            u_a = u_b; u_b = u_c;
+            f_a = f_b; f_b = f_c; f_c = f_d;
+            if (sg == 0) { u_c = ld_pair<0>(U0 + j * kS2P, ci); f_d = ld_pair<0>(Fr + j * kS2P, ci); }
+            else { u_c = ld_pair<1>(U0 + j * kS2P, ci); f_d = ld_pair<1>(Fr + j * kS2P, ci); }
+            // stage A: first sweep at row s-1
+            const int ya = s - 1;
+            double2 p_c = u_b;
+            if ((unsigned)(ya - 1) < (unsigned)(ny - 2)) {
+                const double *row = U0 + ((j + kS2Ring - 1) % kS2Ring) * kS2P + (j & 1);
+                const double xl = row[ci - 1], xr = row[ci + 2];
+                if (i0) p_c.x = u_b.x + k.w * jac_res(u_b.y, xl, u_c.x, u_a.x, u_b.x, f_c.x, k);
+                if (i1) p_c.y = u_b.y + k.w * jac_res(xr, u_b.x, u_c.y, u_a.y, u_b.y, f_c.y, k);
+            }
+            *reinterpret_cast<double2 *>(S1 + ((j + 3) & 3) * kS2P + ci) = p_c;
+            // stage B: second sweep at row s-2
+            const int yb = s - 2;
+            double2 q_c = p_b;
+            if ((unsigned)(yb - 1) < (unsigned)(ny - 2)) {
+                const double *row = S1 + ((j + 2) & 3) * kS2P;
+                const double xl = row[ci - 1], xr = row[ci + 2];
+                if (i0) q_c.x = p_b.x + k.w * jac_res(p_b.y, xl, p_c.x, p_a.x, p_b.x, f_b.x, k);
+                if (i1) q_c.y = p_b.y + k.w * jac_res(xr, p_b.x, p_c.y, p_a.y, p_b.y, f_b.y, k);
+            }
+            *reinterpret_cast<double2 *>(S2 + ((j + 2) & 3) * kS2P + ci) = q_c;
+            // stage C: output row s-3
+            const int yc = s - 3;
+            if ((unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
+                const size_t g = (size_t)x0 + (size_t)nx * yc;
+                if (o0) a.u_out[g] = q_b.x;
+                if (o1) a.u_out[g + 1] = q_b.y;
+                if ((j & 1) == 0 && o0) {  // even row (compile time), x0 even: coarse point (Ic, yc/2)
+                    const int J = yc >> 1;
+                    const size_t pc = (size_t)Ic + (size_t)nxc * J;
+                    a.ec[pc] = 0.0;
+                    const bool jint = (unsigned)(J - 1) < (unsigned)(nyc - 2);
+                    if (cint && jint) {
+                        const double xl = S2[((j + 1) & 3) * kS2P + ci - 1];
+                        const double v = jac_res(q_b.y, xl, q_c.x, q_a.x, q_b.x, f_a.x, k);
+                        a.rc[pc] = v;
+                        if (cmir_lo) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                        if (cmir_hi) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+                    } else if (!(cedge_bc && jint)) {
+                        a.rc[pc] = 0.0;
+                    }
+                }
+            }
+            p_a = p_b; p_b = p_c;
+            q_a = q_b; q_b = q_c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kS2NT) mg_up_stream2_kernel(const TileArgs a, int ch)
+{
+    extern __shared__ __align__(128) unsigned char s2raw[];
+    __shared__ double red[32];
+    double *Us = reinterpret_cast<double *>(s2raw);
+    double *Fr = Us + kS2Ring * kS2P;
+    double *C0 = Fr + kS2Ring * kS2P;
+    double *T1 = C0 + 4 * kS2P;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(T1 + 4 * kS2P);
+    double *Ec = reinterpret_cast<double *>(bars + kS2Ring);  // [kS2CRing][kS2CP]
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double *rhs = a.rhs;
+    double *out = a.u_out;
+    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int t = threadIdx.x, ci = 2 * t + 2;
+    const int X0 = blockIdx.x * kS2W, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);  // ch even
+    const int x0 = X0 - 4 + 2 * t, x1 = x0 + 1;
+    const bool d0 = x0 >= 0 && x0 < nx, d1 = x1 >= 0 && x1 < nx;
+    const bool i0 = x0 >= 1 && x0 <= nx - 2, i1 = x1 >= 1 && x1 <= nx - 2;
+    const bool outt = t >= 2 && t <= kS2NT - 3;
+    const bool o0 = outt && d0, o1 = outt && d1;
+    const int s_begin = Y0 - 2, s_end = Y1 + 1;  // even
+    const int K0 = s_begin >> 1;
+    const int cx0 = X0 / 2 - 3;                  // coarse window origin; local coarse column of x0: t + 1
+    const int Il = t + 1;
+    const bool bc_first = apply_bcs && x0 == 0;       // fine[0,:] = fine[1,:]
+    const bool bc_last = apply_bcs && x0 == nx - 1;   // fine[nx-1,:] = fine[nx-2,:]
+    if (t == 0) {
+        for (int r = 0; r < 4; ++r) {
+            C0[r * kS2P + 0] = C0[r * kS2P + 1] = C0[r * kS2P + kS2P - 2] = C0[r * kS2P + kS2P - 1] = 0.0;
+            T1[r * kS2P + 0] = T1[r * kS2P + 1] = T1[r * kS2P + kS2P - 2] = T1[r * kS2P + kS2P - 1] = 0.0;
+        }
+        for (int r = 0; r < kS2Ring; ++r) mbar_init(&bars[r], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int j = 0; j < kS2D; ++j) stream2_issue_row(Us, Fr, a.u_in, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
+    }
+    // coarse rows: coarse row K0 + m -> slot m % kS2CRing, window columns cx0 .. cx0 + kS2CW - 1 (boundary ring = 0)
+    auto issue_coarse = [&](int m, int slot) {
+        const int K = K0 + m;
+        const bool krow = K >= 1 && K <= nyc - 2;
+        for (int e = t; e < kS2CW; e += kS2NT) {
+            const int I = cx0 + e;
+            const bool in = krow && I >= 1 && I <= nxc - 2;
+            cp_async8(Ec + slot * kS2CP + e, a.ec + (in ? (size_t)I + (size_t)nxc * K : 0), in);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < kS2DC; ++j) {
+        if (j == 0) issue_coarse(0, 0);
+        if (j & 1) issue_coarse((j + 1) >> 1, ((j + 1) >> 1) % kS2CRing);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __syncthreads();
+    double2 z2 = make_double2(0.0, 0.0);
+    double2 c_a = z2, c_b = z2, t_a = z2, t_b = z2, f_a = z2, f_b = z2, f_c = z2;
+    double acc = 0.0;
+    uint32_t phase = 0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kS2Ring, phase ^= 1u) {
+        const int m0 = (s0 - s_begin) >> 1;
+#pragma unroll
+        for (int j = 0; j < kS2Ring; ++j) {
+            const int s = s0 + j;
+            if ((j + kS2DC) & 1) issue_coarse(m0 + ((j + kS2DC + 1) >> 1), ((j + kS2DC + 1) >> 1) % kS2CRing);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kS2DC) : "memory");
+            mbar_wait(&bars[j], phase);
+            __syncthreads();
+            if (t == 0)
+                stream2_issue_row(Us, Fr, a.u_in, rhs, s + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny,
+                                  s_end);
+            f_a = f_b; f_b = f_c;
+            double2 us;
+            if ((j & 1) == 0) { us = ld_pair<0>(Us + j * kS2P, ci); f_c = ld_pair<0>(Fr + j * kS2P, ci); }
+            else { us = ld_pair<1>(Us + j * kS2P, ci); f_c = ld_pair<1>(Fr + j * kS2P, ci); }
+            // stage A: corrected u at row s = u_s - P(ec); x0 is even (coarse column Il), x1 odd (between Il and Il+1)
+            double e0, e1;
+            {
+                const double *r0 = Ec + ((j >> 1) % kS2CRing) * kS2CP + Il, *r1 = Ec + (((j >> 1) + 1) % kS2CRing) * kS2CP + Il;
+                if ((j & 1) == 0) {
+                    e0 = r0[0];
+                    e1 = 0.5 * r0[0] + 0.5 * r0[1];
+                    if (bc_last) e0 = 0.5 * r0[-1] + 0.5 * r0[0];
+                } else {
+                    e0 = 0.5 * r0[0] + 0.5 * r1[0];
+                    e1 = ((0.25 * r0[0] + 0.25 * r0[1]) + 0.25 * r1[0]) + 0.25 * r1[1];
+                    if (bc_last) e0 = ((0.25 * r0[-1] + 0.25 * r0[0]) + 0.25 * r1[-1]) + 0.25 * r1[0];
+                }
+                if (bc_first) e0 = e1;
+            }
+            const double2 c_c = make_double2(us.x - e0, us.y - e1);
+            *reinterpret_cast<double2 *>(C0 + (j & 3) * kS2P + ci) = c_c;
+            // stage B: first post-sweep at row s-1
+            const int yb = s - 1;
+            double2 t_c = c_b;
+            if ((unsigned)(yb - 1) < (unsigned)(ny - 2)) {
+                const double *row = C0 + ((j + 3) & 3) * kS2P;
+                const double xl = row[ci - 1], xr = row[ci + 2];
+                if (i0) t_c.x = c_b.x + k.w * jac_res(c_b.y, xl, c_c.x, c_a.x, c_b.x, f_b.x, k);
+                if (i1) t_c.y = c_b.y + k.w * jac_res(xr, c_b.x, c_c.y, c_a.y, c_b.y, f_b.y, k);
+            }
+            *reinterpret_cast<double2 *>(T1 + ((j + 3) & 3) * kS2P + ci) = t_c;
+            // stage C: second post-sweep at row s-2 -> u, sum of its pre-update res^2
+            const int yc = s - 2;
+            if ((unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
+                double2 v = t_b;
+                if ((unsigned)(yc - 1) < (unsigned)(ny - 2)) {
+                    const double *row = T1 + ((j + 2) & 3) * kS2P;
+                    const double xl = row[ci - 1], xr = row[ci + 2];
+                    if (i0 && o0) {
+                        const double res = jac_res(t_b.y, xl, t_c.x, t_a.x, t_b.x, f_a.x, k);
+                        acc += res * res;
+                        v.x = t_b.x + k.w * res;
+                    }
+                    if (i1 && o1) {
+                        const double res = jac_res(xr, t_b.x, t_c.y, t_a.y, t_b.y, f_a.y, k);
+                        acc += res * res;
+                        v.y = t_b.y + k.w * res;
+                    }
+                }
+                const size_t g = (size_t)x0 + (size_t)nx * yc;
+                if (o0) out[g] = v.x;
+                if (o1) out[g + 1] = v.y;
             }
             c_a = c_b; c_b = c_c;
             t_a = t_b; t_b = t_c;

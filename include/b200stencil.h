@@ -210,7 +210,8 @@ typedef struct {
     int smem_levels;       /* 1: all levels that fit are collapsed into one shared-memory-resident kernel */
     int fuse_sweeps;       /* temporal blocking on the fine levels (2 sweeps + transfer operator per kernel; variant A
                               only, bit-identical to the unfused kernels): 0 off, 1 automatic (streaming y-marching
-                              kernels on large levels, shared-memory tile kernels on small ones), 2 tiles, 3 streaming */
+                              kernels on large levels, shared-memory tile kernels on small ones), 2 tiles everywhere,
+                              3 streaming (one column per thread) everywhere, 4 streaming (two columns) everywhere */
 } b2s_mg_config;
 
 /* preallocate_buffers(nx, ny)  multigrid.jl:25-38 (+ level table, graphs). */
