@@ -198,7 +198,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
         if (use_streaming(l) && two_col) {
             const int ch = stream2_rows(l);
-            mg_down_stream2_kernel<<<stream2_grid(l, ch), kS2NT, kS2SmemDown, st>>>(t, ch);
+            mg_down_stream2_kernel<<<stream2_grid(l, ch), kS2NT + 32, kS2SmemDown, st>>>(t, ch);
         } else if (use_streaming(l)) {
             const int ch = stream_rows(l);
             mg_down_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
@@ -244,7 +244,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
         if (use_streaming(l) && two_col) {
             const int ch = stream2_rows(l);
-            mg_up_stream2_kernel<<<stream2_grid(l, ch), kS2NT, kS2SmemUp, st>>>(t, ch);
+            mg_up_stream2_kernel<<<stream2_grid(l, ch), kS2NT + 32, kS2SmemUp, st>>>(t, ch);
         } else if (use_streaming(l)) {
             const int ch = stream_rows(l);
             mg_up_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);

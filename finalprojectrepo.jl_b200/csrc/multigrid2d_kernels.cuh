@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_up_stream_kerne
 // of the two x neighbours of each point is a register of the same thread, own-column values are read and stage results
 // published as 16-byte pairs, the per-row index/predicate overhead is shared by two points, and a thread carries twice
 // as many independent FP64 dependency chains (the chains, not issue slots or HBM, bound the one-column version:
-// profiles/r01_ncu_source_mg_down_stream.md). Strip = 256 columns (248 outputs + 4 halo columns per side).
+// profiles/r01_ncu_source_mg_down_stream2.md). Strip = 256 columns (248 outputs + 4 halo columns per side).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kS2NT = 128;
 constexpr int kS2W = 2 * kS2NT - 8;   // output columns per strip
@@ -950,7 +950,7 @@ __device__ __forceinline__ double jac_res(double xp, double xm, double yp, doubl
     return ((xp + xm + yp + ym - k.C * c) * k._h2 - f);
 }
 
-__global__ void __launch_bounds__(kS2NT) mg_down_stream2_kernel(const TileArgs a, int ch)
+__global__ void __launch_bounds__(kS2NT + 32) mg_down_stream2_kernel(const TileArgs a, int ch)
 {
     extern __shared__ __align__(128) unsigned char s2raw[];
     double *U0 = reinterpret_cast<double *>(s2raw);       // [kS2Ring][kS2P]
@@ -973,16 +973,34 @@ __global__ void __launch_bounds__(kS2NT) mg_down_stream2_kernel(const TileArgs a
     const bool outt = t >= 2 && t <= kS2NT - 3;
     const bool o0 = outt && d0, o1 = outt && d1;
     const int s_begin = Y0 - 3, s_end = Y1 + 2;
+    // Warp kS2NT/32 is the producer: its lane 0 issues the bulk copies of row s + kS2D while the consumer warps work on
+    // row s, so the (scalar, ~100-instruction) issue path is off the consumers' critical path. It joins the per-row
+    // block barrier, which is what tells it that the ring slot it refills has been read.
+    if (threadIdx.x >= kS2NT) {
+        if (threadIdx.x == kS2NT) {
+            for (int r = 0; r < kS2Ring; ++r) mbar_init(&bars[r], 1);
+            fence_mbar_init();
+            fence_proxy_async();
+#pragma unroll
+            for (int j = 0; j < kS2D; ++j) stream2_issue_row(U0, Fr, u, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
+        }
+        __syncthreads();
+        for (int s0 = s_begin; s0 <= s_end; s0 += kS2Ring) {
+#pragma unroll
+            for (int j = 0; j < kS2Ring; ++j) {
+                __syncthreads();
+                if (threadIdx.x == kS2NT)
+                    stream2_issue_row(U0, Fr, u, rhs, s0 + j + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny,
+                                      s_end);
+            }
+        }
+        return;
+    }
     if (t == 0) {
         for (int r = 0; r < 4; ++r) {
             S1[r * kS2P + 0] = S1[r * kS2P + 1] = S1[r * kS2P + kS2P - 2] = S1[r * kS2P + kS2P - 1] = 0.0;
             S2[r * kS2P + 0] = S2[r * kS2P + 1] = S2[r * kS2P + kS2P - 2] = S2[r * kS2P + kS2P - 1] = 0.0;
         }
-        for (int r = 0; r < kS2Ring; ++r) mbar_init(&bars[r], 1);
-        fence_mbar_init();
-        fence_proxy_async();
-#pragma unroll
-        for (int j = 0; j < kS2D; ++j) stream2_issue_row(U0, Fr, u, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
     }
     __syncthreads();
     const int Ic = x0 >> 1;  // x0 is even: the coarse column this thread writes on even rows
@@ -1001,8 +1019,6 @@ __global__ void __launch_bounds__(kS2NT) mg_down_stream2_kernel(const TileArgs a
             const int sg = (j + kOdd) & 1;  // parity shift of row s (= Y0 - 3 + multiple of kS2Ring + j), of row s-1: j & 1
             mbar_wait(&bars[j], phase);
             __syncthreads();
-            if (t == 0)
-                stream2_issue_row(U0, Fr, u, rhs, s + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny, s_end);
             u_a = u_b; u_b = u_c;
             f_a = f_b; f_b = f_c; f_c = f_d;
             if (sg == 0) { u_c = ld_pair<0>(U0 + j * kS2P, ci); f_d = ld_pair<0>(Fr + j * kS2P, ci); }
@@ -1055,7 +1071,7 @@ __global__ void __launch_bounds__(kS2NT) mg_down_stream2_kernel(const TileArgs a
     }
 }
 
-__global__ void __launch_bounds__(kS2NT) mg_up_stream2_kernel(const TileArgs a, int ch)
+__global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArgs a, int ch)
 {
     extern __shared__ __align__(128) unsigned char s2raw[];
     __shared__ double red[32];
@@ -1086,19 +1102,23 @@ __global__ void __launch_bounds__(kS2NT) mg_up_stream2_kernel(const TileArgs a, 
     const int Il = t + 1;
     const bool bc_first = apply_bcs && x0 == 0;       // fine[0,:] = fine[1,:]
     const bool bc_last = apply_bcs && x0 == nx - 1;   // fine[nx-1,:] = fine[nx-2,:]
-    if (t == 0) {
-        for (int r = 0; r < 4; ++r) {
-            C0[r * kS2P + 0] = C0[r * kS2P + 1] = C0[r * kS2P + kS2P - 2] = C0[r * kS2P + kS2P - 1] = 0.0;
-            T1[r * kS2P + 0] = T1[r * kS2P + 1] = T1[r * kS2P + kS2P - 2] = T1[r * kS2P + kS2P - 1] = 0.0;
-        }
+    const bool producer = threadIdx.x >= kS2NT;  // see mg_down_stream2_kernel
+    if (threadIdx.x == kS2NT) {
         for (int r = 0; r < kS2Ring; ++r) mbar_init(&bars[r], 1);
         fence_mbar_init();
         fence_proxy_async();
 #pragma unroll
         for (int j = 0; j < kS2D; ++j) stream2_issue_row(Us, Fr, a.u_in, rhs, s_begin + j, j, &bars[j], X0, nx, ny, s_end);
     }
+    if (t == 0) {
+        for (int r = 0; r < 4; ++r) {
+            C0[r * kS2P + 0] = C0[r * kS2P + 1] = C0[r * kS2P + kS2P - 2] = C0[r * kS2P + kS2P - 1] = 0.0;
+            T1[r * kS2P + 0] = T1[r * kS2P + 1] = T1[r * kS2P + kS2P - 2] = T1[r * kS2P + kS2P - 1] = 0.0;
+        }
+    }
     // coarse rows: coarse row K0 + m -> slot m % kS2CRing, window columns cx0 .. cx0 + kS2CW - 1 (boundary ring = 0)
     auto issue_coarse = [&](int m, int slot) {
+        if (producer) return;
         const int K = K0 + m;
         const bool krow = K >= 1 && K <= nyc - 2;
         for (int e = t; e < kS2CW; e += kS2NT) {
@@ -1126,11 +1146,15 @@ __global__ void __launch_bounds__(kS2NT) mg_up_stream2_kernel(const TileArgs a, 
             if ((j + kS2DC) & 1) issue_coarse(m0 + ((j + kS2DC + 1) >> 1), ((j + kS2DC + 1) >> 1) % kS2CRing);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kS2DC) : "memory");
+            if (producer) {
+                __syncthreads();
+                if (threadIdx.x == kS2NT)
+                    stream2_issue_row(Us, Fr, a.u_in, rhs, s + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny,
+                                      s_end);
+                continue;
+            }
             mbar_wait(&bars[j], phase);
             __syncthreads();
-            if (t == 0)
-                stream2_issue_row(Us, Fr, a.u_in, rhs, s + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny,
-                                  s_end);
             f_a = f_b; f_b = f_c;
             double2 us;
             if ((j & 1) == 0) { us = ld_pair<0>(Us + j * kS2P, ci); f_c = ld_pair<0>(Fr + j * kS2P, ci); }
