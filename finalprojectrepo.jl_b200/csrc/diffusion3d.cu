@@ -26,10 +26,18 @@ static int env_int(const char *name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
-static int tma_choice_index()
+// Tile shape by problem size (measured on B200, profiles/r01_small_grid_configs.log): small, L2-resident grids are
+// latency-bound and prefer many small blocks; 512^3 streams from HBM and prefers 128x8 tiles.
+static int tma_choice_index(size_t cells = 0)
 {
-    int c = env_int("B2S_TMA_CFG", 0);
-    return (c >= 0 && c < kNumTmaChoices) ? c : 0;
+    const char *s = getenv("B2S_TMA_CFG");
+    if (s && *s) {
+        const int c = atoi(s);
+        return (c >= 0 && c < kNumTmaChoices) ? c : 0;
+    }
+    if (cells > 0 && cells <= (size_t)192 * 192 * 192) return 1;  // 64 x 8
+    if (cells > 0 && cells <= (size_t)384 * 384 * 384) return 3;  // 128 x 4
+    return 0;                                                      // 128 x 8
 }
 
 template <int TX, int TY, int S>
@@ -94,8 +102,8 @@ static int pick_zchunk(int nxy_tiles, int nz, int max_blocks)
     if (zc <= 0) {
         const int want_blocks = 148 * 8;
         int chunks = (want_blocks + nxy_tiles - 1) / nxy_tiles;
-        chunks = std::max(chunks, (interior + 32) / 64);  // measured on B200: ~64 planes per chunk is the sweet spot
-        chunks = std::max(1, std::min(chunks, interior / 16 > 0 ? interior / 16 : 1));
+        chunks = std::max(chunks, (interior + 32) / 64);  // measured on B200: ~64 planes per chunk is the sweet spot at 512^3
+        chunks = std::max(1, std::min(chunks, interior / 8 > 0 ? interior / 8 : 1));
         zc = (interior + chunks - 1) / chunks;
     }
     zc = std::max(1, std::min(zc, interior));
@@ -142,7 +150,7 @@ extern "C" int b2s_diffusion3d_step_tau(const double *Ht, const double *Htau, do
     if (use_tma) {
         B2S_REQUIRE(nx % 2 == 0 && (((uintptr_t)Ht | (uintptr_t)Htau | (uintptr_t)Htau2 | (uintptr_t)dHdtau) & 15) == 0,
                     B2S_ERR_BAD_ARG, "TMA variant needs even nx and 16-byte aligned fields");
-        const int ch = tma_choice_index();
+        const int ch = tma_choice_index((size_t)nx * ny * nz);
         const TmaChoice &c = kTmaChoices[ch];
         p.zchunk = pick_zchunk(((nx + c.tx - 1) / c.tx) * ((ny + c.ty - 1) / c.ty), nz, kMaxPartials);
         CUtensorMap mA, mH;
@@ -521,7 +529,7 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
         }
         h->use_tma = kv == B2S_KERNEL_TMA || (kv == B2S_KERNEL_AUTO && elig && h->ar.cells >= (size_t)64 * 64 * 64);
         if (h->use_tma) {
-            h->tma_choice = tma_choice_index();
+            h->tma_choice = tma_choice_index(h->ar.cells);
             const TmaChoice &c = kTmaChoices[h->tma_choice];
             h->zchunk = pick_zchunk(((cfg->nx + c.tx - 1) / c.tx) * ((cfg->ny + c.ty - 1) / c.ty), cfg->nz, kMaxPartials);
             h->nblocks = grid_blocks_tma(h->tma_choice, cfg->nx, cfg->ny, cfg->nz, h->zchunk);

@@ -55,6 +55,7 @@ struct b2s_mg {
     double last_ms = 0.0;
     int tile_choice = 0;
     int stream_ch = 0;
+    size_t stream_min_points = 1500000;  // levels above this use the streaming kernels (B2S_MG_STREAM_MIN)
     long long *prof_dev = nullptr;  // B2S_MG_PROF=1: phase stamps of the collapsed coarse kernel
     bool coarse_global = false;     // coarsest level too large for shared memory: solved by global-memory kernels
     CoarseLoop *loop_dev = nullptr, *loop_pin = nullptr;
@@ -164,7 +165,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     auto use_streaming = [&](int l) {
         if (c.fuse_sweeps == 2) return false;
         if (c.fuse_sweeps == 3 || c.fuse_sweeps == 4) return true;
-        return (size_t)h->nx[l] * h->ny[l] > (size_t)1500000;
+        return (size_t)h->nx[l] * h->ny[l] > h->stream_min_points;
     };
     const bool two_col = c.fuse_sweeps != 3;  // 1 (auto) and 4: two columns per thread; 3: one column per thread
     auto stream2_rows = [&](int l) {
@@ -590,6 +591,8 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         MG_CUDA(cudaFuncSetAttribute(mg_up_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemUp));
         const char *e2 = getenv("B2S_MG_CH");
         h->stream_ch = (e2 && *e2) ? atoi(e2) : 0;
+        const char *e4 = getenv("B2S_MG_STREAM_MIN");
+        if (e4 && *e4) h->stream_min_points = (size_t)atoll(e4);
         const char *e3 = getenv("B2S_MG_PROF");
         if (e3 && *e3 == '1') {
             MG_CUDA(cudaMalloc(&h->prof_dev, 64 * sizeof(long long)));

@@ -9,6 +9,6 @@ for N in 8 4 2; do
 done
 timeout 300 python bench.py --gpus 1 --steps 3 --warmup 3 --no-mg --no-cpu-baseline >> gpurun_out/r1o_scale.jsonl 2>> gpurun_out/r1o_scale.err
 echo "N=1 exit $?" >> gpurun_out/r1o_info.txt
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29590 scripts/mp_diffusion_check.py 64 64 34 0 tma > gpurun_out/r1o_mpcheck.log 2>&1
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29590 tests/mp_diffusion_check.py 64 64 34 0 tma > gpurun_out/r1o_mpcheck.log 2>&1
 echo "mpcheck exit $?" >> gpurun_out/r1o_info.txt
 true

@@ -1,7 +1,7 @@
 """One process per GPU (torchrun): z-slab diffusion with the fused NVLink halo push + peer-store norm exchange, checked
 against the oracle's rank emulation. Every rank verifies its own slab bit-for-bit. Usage (2+ GPUs):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      scripts/mp_diffusion_check.py [nx ny nz] [halo_mode]
+      tests/mp_diffusion_check.py [nx ny nz] [halo_mode]
 """
 import os
 import sys

@@ -45,7 +45,7 @@ def test_one_process_per_gpu_matches_rank_emulation(b2s, gpu, args):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29541",
-                        os.path.join(ROOT, "scripts", "mp_diffusion_check.py")] + args,
+                        os.path.join(ROOT, "tests", "mp_diffusion_check.py")] + args,
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for k in range(n):
