@@ -48,17 +48,24 @@ def parse():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -77,11 +84,18 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        import datetime
         sm, mx, reasons = [], None, set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
+            try:  # keep only the samples taken inside the timed region (the sampler is started before the warm-up)
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and self.t1 is not None and not (self.t0 - 0.05 <= ts <= self.t1 + 0.05):
+                    continue
+            except ValueError:
+                pass
             try:
                 sm.append(float(f[1])); mx = float(f[2])
             except ValueError:
@@ -253,13 +267,14 @@ def main():
     cells = float(n - 2) ** 3
     iters = args.iters
     # ---- device-resident measurement ------------------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        s.iterate(iters, want_hist=False)
     sampler = ClockSampler(dev)
-    launches0, _ = s.stats()
-    sync_all()
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        s.iterate(iters, want_hist=False)
+    launches0, _ = s.stats()
+    sync_all()
+    sampler.mark_start()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -267,6 +282,7 @@ def main():
         dev_ms += s.stats()[1]  # CUDA events on the launching stream, inside the library
     sync_all()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches1, _ = s.stats()
     dev_ms = max_over_ranks(dev_ms)
