@@ -1117,21 +1117,23 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
         }
     }
     // coarse rows: coarse row K0 + m -> slot m % kS2CRing, window columns cx0 .. cx0 + kS2CW - 1 (boundary ring = 0)
+    // (loaded by the 32 lanes of the producer warp with cp.async; its wait_group + the per-row barrier publish them)
     auto issue_coarse = [&](int m, int slot) {
-        if (producer) return;
         const int K = K0 + m;
         const bool krow = K >= 1 && K <= nyc - 2;
-        for (int e = t; e < kS2CW; e += kS2NT) {
+        for (int e = (int)threadIdx.x - kS2NT; e < kS2CW; e += 32) {
             const int I = cx0 + e;
             const bool in = krow && I >= 1 && I <= nxc - 2;
             cp_async8(Ec + slot * kS2CP + e, a.ec + (in ? (size_t)I + (size_t)nxc * K : 0), in);
         }
     };
+    if (producer) {
 #pragma unroll
-    for (int j = 0; j < kS2DC; ++j) {
-        if (j == 0) issue_coarse(0, 0);
-        if (j & 1) issue_coarse((j + 1) >> 1, ((j + 1) >> 1) % kS2CRing);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int j = 0; j < kS2DC; ++j) {
+            if (j == 0) issue_coarse(0, 0);
+            if (j & 1) issue_coarse((j + 1) >> 1, ((j + 1) >> 1) % kS2CRing);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     }
     __syncthreads();
     double2 z2 = make_double2(0.0, 0.0);
@@ -1143,10 +1145,10 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
 #pragma unroll
         for (int j = 0; j < kS2Ring; ++j) {
             const int s = s0 + j;
-            if ((j + kS2DC) & 1) issue_coarse(m0 + ((j + kS2DC + 1) >> 1), ((j + kS2DC + 1) >> 1) % kS2CRing);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(kS2DC) : "memory");
             if (producer) {
+                if ((j + kS2DC) & 1) issue_coarse(m0 + ((j + kS2DC + 1) >> 1), ((j + kS2DC + 1) >> 1) % kS2CRing);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group %0;" ::"n"(kS2DC) : "memory");  // coarse rows of fine row s have landed
                 __syncthreads();
                 if (threadIdx.x == kS2NT)
                     stream2_issue_row(Us, Fr, a.u_in, rhs, s + kS2D, (j + kS2D) % kS2Ring, &bars[(j + kS2D) % kS2Ring], X0, nx, ny,
