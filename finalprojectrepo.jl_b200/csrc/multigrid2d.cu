@@ -55,6 +55,8 @@ struct b2s_mg {
     double last_ms = 0.0;
     int tile_choice = 0;
     int stream_ch = 0;
+    bool stream_warp = false;            // automatic mode: block-wide two-column streaming kernels (measured faster than the
+                                         // one-warp-per-strip variant; B2S_MG_STREAM_KIND=warp selects the latter)
     size_t stream_min_points = 1500000;  // levels above this use the streaming kernels (B2S_MG_STREAM_MIN)
     long long *prof_dev = nullptr;  // B2S_MG_PROF=1: phase stamps of the collapsed coarse kernel
     bool coarse_global = false;     // coarsest level too large for shared memory: solved by global-memory kernels
@@ -164,10 +166,23 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     // 2 = tiles everywhere, 3 = streaming everywhere
     auto use_streaming = [&](int l) {
         if (c.fuse_sweeps == 2) return false;
-        if (c.fuse_sweeps == 3 || c.fuse_sweeps == 4) return true;
+        if (c.fuse_sweeps == 3 || c.fuse_sweeps == 4 || c.fuse_sweeps == 5) return true;
         return (size_t)h->nx[l] * h->ny[l] > h->stream_min_points;
     };
     const bool two_col = c.fuse_sweeps != 3;  // 1 (auto) and 4: two columns per thread; 3: one column per thread
+    const bool warp_kind = c.fuse_sweeps == 5 || (c.fuse_sweeps == 1 && h->stream_warp);  // one warp per strip
+    auto warp_rows = [&](int l) {
+        const int bx = (h->nx[l] + kWW - 1) / kWW, ny = h->ny[l], slots = 148 * 28;
+        int ch = 16;
+        for (int w = 1; w <= 64; ++w) {
+            const int chunks = std::max(1, (w * slots) / bx);
+            ch = (ny + chunks - 1) / chunks;
+            if (ch <= 256) break;
+        }
+        if (h->stream_ch > 0) ch = h->stream_ch;
+        return std::max(16, (ch + 1) & ~1);
+    };
+    auto warp_grid = [&](int l, int ch) { return dim3((h->nx[l] + kWW - 1) / kWW, (h->ny[l] + ch - 1) / ch, 1); };
     auto stream2_rows = [&](int l) {
         const int bx = (h->nx[l] + kS2W - 1) / kS2W, ny = h->ny[l], slots = 148 * 4;
         int ch = 16;
@@ -197,7 +212,10 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = 0; l < fs && fused; ++l) {
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
-        if (use_streaming(l) && two_col) {
+        if (use_streaming(l) && warp_kind) {
+            const int ch = warp_rows(l);
+            mg_down_warp_kernel<<<warp_grid(l, ch), 32, 0, st>>>(t, ch);
+        } else if (use_streaming(l) && two_col) {
             const int ch = stream2_rows(l);
             mg_down_stream2_kernel<<<stream2_grid(l, ch), kS2NT + 32, kS2SmemDown, st>>>(t, ch);
         } else if (use_streaming(l)) {
@@ -243,7 +261,10 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        if (use_streaming(l) && two_col) {
+        if (use_streaming(l) && warp_kind) {
+            const int ch = warp_rows(l);
+            mg_up_warp_kernel<<<warp_grid(l, ch), 32, 0, st>>>(t, ch);
+        } else if (use_streaming(l) && two_col) {
             const int ch = stream2_rows(l);
             mg_up_stream2_kernel<<<stream2_grid(l, ch), kS2NT + 32, kS2SmemUp, st>>>(t, ch);
         } else if (use_streaming(l)) {
@@ -593,6 +614,8 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         h->stream_ch = (e2 && *e2) ? atoi(e2) : 0;
         const char *e4 = getenv("B2S_MG_STREAM_MIN");
         if (e4 && *e4) h->stream_min_points = (size_t)atoll(e4);
+        const char *e5 = getenv("B2S_MG_STREAM_KIND");
+        if (e5 && *e5) h->stream_warp = (strcmp(e5, "warp") == 0);
         const char *e3 = getenv("B2S_MG_PROF");
         if (e3 && *e3 == '1') {
             MG_CUDA(cudaMalloc(&h->prof_dev, 64 * sizeof(long long)));

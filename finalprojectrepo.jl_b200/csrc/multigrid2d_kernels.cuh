@@ -1223,6 +1223,251 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-warp-per-strip streaming kernels: the same two fused level passes with NO block barrier and NO shared-memory
+// exchange between the pipeline stages. A block is a single warp that owns 64 columns (56 outputs + 4 halo columns
+// per side, two columns per lane) and a chunk of rows. Input rows arrive through an 8-row bulk-copy ring (lane 0 refills
+// the slot it has just consumed; completion on one mbarrier per slot); every stage keeps the y neighbours of its two
+// columns in registers and gets the x neighbours of the previous stage from the adjacent lanes by warp shuffles. With
+// ~9 KB of shared memory and one warp per block, 21-25 independent warps are resident per SM (the block-wide variants: 16
+// consumer warps coupled four at a time by a barrier per row). Same arithmetic per point -> bit-identical results.
+// Measured on B200 it is SLOWER than the block-wide two-column kernels (4097^2: 0.427 vs 0.358 ms per V-cycle): the
+// 512-byte bulk copies and the 14 % halo overhead cost more than the barriers; kept as fuse_sweeps = 5 for comparison.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWW = 56;      // output columns per strip
+constexpr int kWRing = 8;    // ring rows = prefetch depth = unroll factor
+constexpr int kWP = 68;      // ring pitch: 2 pad + 64 columns + parity shift + pad (even)
+
+// lane 0: bulk-copy row r of two fields for the 64-column strip starting at column X0-4 (see stream_issue_row)
+__device__ __forceinline__ void warp_issue_row(double *dstA, double *dstB, const double *gA, const double *gB, int r, uint64_t *bar,
+                                               int X0, int nx, int ny, int r_last)
+{
+    if (r < 0 || r >= ny || r > r_last) { mbar_arrive_plain(bar); return; }
+    const int x_lo = max(X0 - 4, 0), x_hi = min(X0 + 59, nx - 1);
+    long long g0 = (long long)x_lo + (long long)nx * r;
+    const int shift = (int)(g0 & 1);
+    g0 -= shift;
+    int n_el = ((x_hi - x_lo + 1) + shift + 1) & ~1;
+    const long long total = (long long)nx * ny;
+    const int dst = (x_lo - shift) - (X0 - 4) + 2 + (r & 1);
+    if (g0 + n_el > total) {  // last element of the array: fetched by hand (the pair would overrun)
+        n_el -= 2;
+        dstA[dst + n_el] = gA[total - 1];
+        dstB[dst + n_el] = gB[total - 1];
+    }
+    if (n_el <= 0) { mbar_arrive_plain(bar); return; }
+    const uint32_t bytes = (uint32_t)n_el * 8u;
+    mbar_arrive_expect_tx(bar, 2u * bytes);
+    bulk_copy_g2s(dstA + dst, gA + g0, bytes, bar);
+    bulk_copy_g2s(dstB + dst, gB + g0, bytes, bar);
+}
+
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+__global__ void __launch_bounds__(32) mg_down_warp_kernel(const TileArgs a, int ch)
+{
+    __shared__ __align__(128) double U0[kWRing][kWP], Fr[kWRing][kWP];
+    __shared__ uint64_t bars[kWRing];
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double *u = a.u_in, *rhs = a.rhs;
+    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int lane = threadIdx.x, ci = 2 * lane + 2;
+    const int X0 = blockIdx.x * kWW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);
+    const int x0 = X0 - 4 + 2 * lane, x1 = x0 + 1;
+    const bool d0 = x0 >= 0 && x0 < nx, d1 = x1 >= 0 && x1 < nx;
+    const bool i0 = x0 >= 1 && x0 <= nx - 2, i1 = x1 >= 1 && x1 <= nx - 2;
+    const bool outl = lane >= 2 && lane <= 29;
+    const bool o0 = outl && d0, o1 = outl && d1;
+    const int s_begin = Y0 - 3, s_end = Y1 + 2;
+    if (lane == 0) {
+        for (int r = 0; r < kWRing; ++r) mbar_init(&bars[r], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int j = 0; j < kWRing; ++j) warp_issue_row(U0[j], Fr[j], u, rhs, s_begin + j, &bars[j], X0, nx, ny, s_end);
+    }
+    __syncwarp();
+    const int Ic = x0 >> 1;
+    const bool cint = Ic >= 1 && Ic <= nxc - 2;
+    const bool cmir_lo = apply_bcs && Ic == 1, cmir_hi = apply_bcs && Ic == nxc - 2;
+    const bool cedge_bc = apply_bcs && (Ic == 0 || Ic == nxc - 1);
+    double2 z2 = make_double2(0.0, 0.0);
+    double2 u_a = z2, u_b = z2, u_c = z2, p_a = z2, p_b = z2, q_a = z2, q_b = z2, f_a = z2, f_b = z2, f_c = z2, f_d = z2;
+    uint32_t phase = 0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kWRing, phase ^= 1u) {
+#pragma unroll
+        for (int j = 0; j < kWRing; ++j) {
+            const int s = s0 + j;
+            mbar_wait(&bars[j], phase);
+            u_a = u_b; u_b = u_c;
+            f_a = f_b; f_b = f_c; f_c = f_d;
+            if (((j + 1) & 1) == 0) { u_c = ld_pair<0>(U0[j], ci); f_d = ld_pair<0>(Fr[j], ci); }  // parity of row s: (j+1)&1
+            else { u_c = ld_pair<1>(U0[j], ci); f_d = ld_pair<1>(Fr[j], ci); }
+            // stage A: first sweep at row s-1 (x neighbours of the row live in the adjacent lanes)
+            double xl = shfl_up1(u_b.y), xr = shfl_dn1(u_b.x);
+            double2 p_c = u_b;
+            if ((unsigned)(s - 2) < (unsigned)(ny - 2)) {
+                if (i0) p_c.x = u_b.x + k.w * jac_res(u_b.y, xl, u_c.x, u_a.x, u_b.x, f_c.x, k);
+                if (i1) p_c.y = u_b.y + k.w * jac_res(xr, u_b.x, u_c.y, u_a.y, u_b.y, f_c.y, k);
+            }
+            // the loaded values have been consumed: refill the slot with row s + kWRing
+            __syncwarp();
+            if (lane == 0) warp_issue_row(U0[j], Fr[j], u, rhs, s + kWRing, &bars[j], X0, nx, ny, s_end);
+            // stage B: second sweep at row s-2
+            xl = shfl_up1(p_b.y); xr = shfl_dn1(p_b.x);
+            double2 q_c = p_b;
+            if ((unsigned)(s - 3) < (unsigned)(ny - 2)) {
+                if (i0) q_c.x = p_b.x + k.w * jac_res(p_b.y, xl, p_c.x, p_a.x, p_b.x, f_b.x, k);
+                if (i1) q_c.y = p_b.y + k.w * jac_res(xr, p_b.x, p_c.y, p_a.y, p_b.y, f_b.y, k);
+            }
+            // stage C: output row s-3
+            const int yc = s - 3;
+            xl = shfl_up1(q_b.y);
+            if ((unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
+                const size_t g = (size_t)x0 + (size_t)nx * yc;
+                if (o0) a.u_out[g] = q_b.x;
+                if (o1) a.u_out[g + 1] = q_b.y;
+                if ((j & 1) == 0 && o0) {  // even row (compile time), x0 even: coarse point (Ic, yc/2)
+                    const int J = yc >> 1;
+                    const size_t pc = (size_t)Ic + (size_t)nxc * J;
+                    a.ec[pc] = 0.0;
+                    const bool jint = (unsigned)(J - 1) < (unsigned)(nyc - 2);
+                    if (cint && jint) {
+                        const double v = jac_res(q_b.y, xl, q_c.x, q_a.x, q_b.x, f_a.x, k);
+                        a.rc[pc] = v;
+                        if (cmir_lo) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                        if (cmir_hi) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+                    } else if (!(cedge_bc && jint)) {
+                        a.rc[pc] = 0.0;
+                    }
+                }
+            }
+            p_a = p_b; p_b = p_c;
+            q_a = q_b; q_b = q_c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) mg_up_warp_kernel(const TileArgs a, int ch)
+{
+    __shared__ __align__(128) double Us[kWRing][kWP], Fr[kWRing][kWP];
+    __shared__ uint64_t bars[kWRing];
+    __shared__ double red[32];
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double *rhs = a.rhs;
+    double *out = a.u_out;
+    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int lane = threadIdx.x, ci = 2 * lane + 2;
+    const int X0 = blockIdx.x * kWW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);  // ch even
+    const int x0 = X0 - 4 + 2 * lane, x1 = x0 + 1;
+    const bool d0 = x0 >= 0 && x0 < nx, d1 = x1 >= 0 && x1 < nx;
+    const bool i0 = x0 >= 1 && x0 <= nx - 2, i1 = x1 >= 1 && x1 <= nx - 2;
+    const bool outl = lane >= 2 && lane <= 29;
+    const bool o0 = outl && d0, o1 = outl && d1;
+    const int s_begin = Y0 - 2, s_end = Y1 + 1;  // even
+    const bool bc_first = apply_bcs && x0 == 0, bc_last = apply_bcs && x0 == nx - 1;
+    if (lane == 0) {
+        for (int r = 0; r < kWRing; ++r) mbar_init(&bars[r], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+#pragma unroll
+        for (int j = 0; j < kWRing; ++j) warp_issue_row(Us[j], Fr[j], a.u_in, rhs, s_begin + j, &bars[j], X0, nx, ny, s_end);
+    }
+    __syncwarp();
+    // coarse correction: this lane's coarse column I = x0/2 (x0 is even), rows K; the boundary ring counts as 0. Each lane
+    // loads its own column straight into registers, three coarse rows ahead; column I+1 / I-1 come from the adjacent lanes.
+    const int Ic = x0 >> 1;
+    const bool cin = Ic >= 1 && Ic <= nxc - 2;
+    const double *gc = a.ec + (cin ? Ic : 0);
+    auto load_coarse = [&](int K) -> double {
+        return (cin && K >= 1 && K <= nyc - 2) ? gc[(size_t)nxc * K] : 0.0;
+    };
+    const int K0 = s_begin >> 1;
+    double cA = load_coarse(K0), cB = load_coarse(K0 + 1), cC = load_coarse(K0 + 2), cD = load_coarse(K0 + 3);
+    double2 z2 = make_double2(0.0, 0.0);
+    double2 c_a = z2, c_b = z2, t_a = z2, t_b = z2, f_a = z2, f_b = z2, f_c = z2;
+    double acc = 0.0;
+    uint32_t phase = 0;
+    for (int s0 = s_begin; s0 <= s_end; s0 += kWRing, phase ^= 1u) {
+        const int Kb = (s0 >> 1);  // coarse row of fine row s0 (s0 even)
+#pragma unroll
+        for (int j = 0; j < kWRing; ++j) {
+            const int s = s0 + j;
+            mbar_wait(&bars[j], phase);
+            f_a = f_b; f_b = f_c;
+            double2 us;
+            if ((j & 1) == 0) { us = ld_pair<0>(Us[j], ci); f_c = ld_pair<0>(Fr[j], ci); }
+            else { us = ld_pair<1>(Us[j], ci); f_c = ld_pair<1>(Fr[j], ci); }
+            // stage A: corrected u at row s. cA = coarse row s>>1, cB = the next one (this lane's column)
+            const double a1 = shfl_dn1(cA), b1 = shfl_dn1(cB), am = shfl_up1(cA), bm = shfl_up1(cB);
+            double e0, e1;
+            if ((j & 1) == 0) {
+                e0 = cA;
+                e1 = 0.5 * cA + 0.5 * a1;
+                if (bc_last) e0 = 0.5 * am + 0.5 * cA;
+            } else {
+                e0 = 0.5 * cA + 0.5 * cB;
+                e1 = ((0.25 * cA + 0.25 * a1) + 0.25 * cB) + 0.25 * b1;
+                if (bc_last) e0 = ((0.25 * am + 0.25 * cA) + 0.25 * bm) + 0.25 * cB;
+            }
+            if (bc_first) e0 = e1;
+            const double2 c_c = make_double2(us.x - e0, us.y - e1);
+            if (j & 1) {  // the next fine row starts the next coarse row
+                cA = cB; cB = cC; cC = cD;
+                cD = load_coarse(Kb + (j >> 1) + 4);
+            }
+            __syncwarp();
+            if (lane == 0) warp_issue_row(Us[j], Fr[j], a.u_in, rhs, s + kWRing, &bars[j], X0, nx, ny, s_end);
+            // stage B: first post-sweep at row s-1
+            double xl = shfl_up1(c_b.y), xr = shfl_dn1(c_b.x);
+            double2 t_c = c_b;
+            if ((unsigned)(s - 2) < (unsigned)(ny - 2)) {
+                if (i0) t_c.x = c_b.x + k.w * jac_res(c_b.y, xl, c_c.x, c_a.x, c_b.x, f_b.x, k);
+                if (i1) t_c.y = c_b.y + k.w * jac_res(xr, c_b.x, c_c.y, c_a.y, c_b.y, f_b.y, k);
+            }
+            // stage C: second post-sweep at row s-2 -> u, sum of its pre-update res^2
+            const int yc = s - 2;
+            xl = shfl_up1(t_b.y); xr = shfl_dn1(t_b.x);
+            if ((unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
+                double2 v = t_b;
+                if ((unsigned)(yc - 1) < (unsigned)(ny - 2)) {
+                    if (i0 && o0) {
+                        const double res = jac_res(t_b.y, xl, t_c.x, t_a.x, t_b.x, f_a.x, k);
+                        acc += res * res;
+                        v.x = t_b.x + k.w * res;
+                    }
+                    if (i1 && o1) {
+                        const double res = jac_res(xr, t_b.x, t_c.y, t_a.y, t_b.y, f_a.y, k);
+                        acc += res * res;
+                        v.y = t_b.y + k.w * res;
+                    }
+                }
+                const size_t g = (size_t)x0 + (size_t)nx * yc;
+                if (o0) out[g] = v.x;
+                if (o1) out[g + 1] = v.y;
+            }
+            c_a = c_b; c_b = c_c;
+            t_a = t_b; t_b = t_c;
+        }
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+    }
+}
+
 // apply_boundary_conditions!(T): Dirichlet T[:,0]=1, T[:,ny-1]=0, then Neumann T[0,:]=T[1,:], T[nx-1,:]=T[nx-2,:]
 // (part2_utils.jl:21-39). kind: 0 both, 1 Dirichlet only, 2 Neumann only.
 __global__ void mg_bc_kernel(const MGCall *cp, double *T, int nx, int ny, int kind)

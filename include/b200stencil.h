@@ -211,7 +211,8 @@ typedef struct {
     int fuse_sweeps;       /* temporal blocking on the fine levels (2 sweeps + transfer operator per kernel; variant A
                               only, bit-identical to the unfused kernels): 0 off, 1 automatic (streaming y-marching
                               kernels on large levels, shared-memory tile kernels on small ones), 2 tiles everywhere,
-                              3 streaming (one column per thread) everywhere, 4 streaming (two columns) everywhere */
+                              3 block-wide streaming (one column per thread) everywhere, 4 block-wide streaming (two
+                              columns per thread, producer warp) everywhere, 5 one-warp-per-strip streaming everywhere */
 } b2s_mg_config;
 
 /* preallocate_buffers(nx, ny)  multigrid.jl:25-38 (+ level table, graphs). */

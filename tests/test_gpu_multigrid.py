@@ -106,6 +106,7 @@ CONFIGS = [
     dict(fuse_sweeps=2),                                # shared-memory tile variant of the fused level kernels
     dict(fuse_sweeps=3),                                # streaming variant (one column per thread) on every level
     dict(fuse_sweeps=4),                                # streaming variant (two columns per thread) on every level
+    dict(fuse_sweeps=5),                                # one-warp-per-strip streaming variant on every level
     dict(use_graph=False),
     dict(use_graph=False, fuse_sweeps=False, smem_levels=False),
     dict(smem_levels=False),
@@ -371,7 +372,7 @@ def test_full_size_properties(p2):
         b = rnd((n, n), 1)
         db = p2.to_device(b)
         outs = []
-        for use_graph, fuse in ((True, 1), (False, 2), (True, 0), (True, 3), (True, 4)):
+        for use_graph, fuse in ((True, 1), (False, 2), (True, 0), (True, 3), (True, 4), (True, 5)):
             x = p2.zeros(n, n)
             r, nc = p2.MGsolve_2DPoisson(x, db, 1.0 / (n - 1), 0.0, 1e-6, 100, False,
                                          opt=p2.MGOpt(use_graph=use_graph, fuse_sweeps=fuse), return_cycles=True)
