@@ -236,3 +236,42 @@ def test_512_properties(b2s, gpu):
     sub = Ha[200:312:7, 200:312:7, 200:312:7]
     assert np.array_equal(sub, sub.transpose(1, 0, 2))  # (x-term + y-term) commutes -> bitwise x<->y symmetry
     assert np.allclose(sub, sub.transpose(2, 1, 0), rtol=1e-12, atol=0)
+
+
+def test_c_level_run_set_initial_state_io_and_device_ptrs(b2s, gpu, oracle):
+    """Remaining L1 entry points: b2s_diff3d_run (whole time loop in C), set_initial, upload/download_state, device_ptr
+    (the L0 kernel applied to the handle's own arrays reproduces the handle's iteration)."""
+    import torch
+    from b200stencil import capi
+    n = (32, 32, 32)
+    g = _mk(b2s, *n)
+    g.init_gaussian()
+    assert g.run(ttot=1.0, tol=1e-8) == [188, 187, 185, 184, 183]
+    g.close()
+    # set_initial with the oracle's initial field == init_gaussian
+    o = oracle.Diffusion3D(*n)
+    g = _mk(b2s, *n)
+    g.set_initial(o.get("Ht"))
+    assert np.allclose(g.iterate(11), o.iterate(11), rtol=REL_NORM_TOL, atol=0)
+    assert np.array_equal(g.get("Htau"), o.get("Htau"))
+    # state download / upload round trip through pinned host memory
+    host = torch.empty(n[0] * n[1] * n[2], dtype=torch.float64).pin_memory()
+    g.download_state(host)
+    assert np.array_equal(host.numpy().reshape(n, order="F"), o.get("Htau"))
+    g.upload_state(host)  # Ht := Htau := host
+    assert np.array_equal(g.get("Ht"), o.get("Htau")) and np.array_equal(g.get("Htau"), o.get("Htau"))
+    # L0 kernel on the handle's device arrays: one more iteration by hand equals iterate(1)
+    Ht, A, B = g.device_ptr("Ht"), g.device_ptr("Htau"), g.device_ptr("Htau2")
+    ref = _mk(b2s, *n)
+    ref.set_initial(g.get("Ht"))
+    e_ref = ref.iterate(1)
+    tS = torch.zeros(1, dtype=torch.float64, device="cuda:0")
+    capi.check(capi.lib().b2s_diffusion3d_step_tau(capi.ptr(Ht), capi.ptr(A), capi.ptr(B), None, n[0], n[1], n[2], g.dtau,
+                                                   1.0 / g.dt, 1.0 / g.dx, 1.0 / g.dy, 1.0 / g.dz, 1.0 / g.dx, 1.0 / g.dy,
+                                                   1.0 / g.dz, g.dt, capi.ptr(tS), capi.KERNEL_AUTO, None))
+    torch.cuda.synchronize()
+    inner = (slice(1, -1),) * 3  # the kernel never writes boundary cells; the two handles' buffers carry different faces (D6)
+    assert np.array_equal(g.get("Htau2")[inner], ref.get("Htau")[inner])
+    err = np.sqrt(tS.item()) / np.sqrt(g.total_N)
+    assert abs(err - e_ref[0]) <= REL_NORM_TOL * err
+    g.close(); ref.close()
