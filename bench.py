@@ -183,6 +183,11 @@ def mg_bench(device, peak):
         out = part2.bench_vcycle(device=device, hbm_peak_gbs=peak)
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {e}"}
+    try:  # config #2's second smoother: red-black Gauss-Seidel + full weighting (variant B), same shape and byte models
+        vb = part2.bench_vcycle(device=device, hbm_peak_gbs=peak, opt=part2.MGOpt(smoother=1, restriction=1))
+        out["variant_b_rbgs_fw"] = vb["sizes"]
+    except Exception as e:  # pragma: no cover
+        out["variant_b_rbgs_fw"] = {"unavailable": f"{type(e).__name__}: {e}"}
     try:
         out["navier_stokes_2049"] = part2.bench_navier_stokes(device=device)
     except Exception as e:  # pragma: no cover

@@ -5,6 +5,7 @@
 // Reference entry points mirrored: MGsolve_2DPoisson! / Vcycle_2DPoisson! (scripts-part2/multigrid.jl:41-170),
 // cg! (scripts-part2/krylov.jl:55-91).
 #include "multigrid2d_kernels.cuh"
+#include "multigrid2d_rb_kernels.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -54,6 +55,7 @@ struct b2s_mg {
     long long launches_per_cycle = 0;
     double last_ms = 0.0;
     int tile_choice = 0;
+    int rb_tile_choice = -1;
     int stream_ch = 0;
     bool stream_warp = false;            // automatic mode: block-wide two-column streaming kernels (measured faster than the
                                          // one-warp-per-strip variant; B2S_MG_STREAM_KIND=warp selects the latter)
@@ -105,6 +107,55 @@ cudaError_t tile_set_attr(int choice)
     }
 }
 
+// variant B (red-black Gauss-Seidel + full weighting) tile kernels; B2S_MG_RB_TILE selects the shape
+template <int TW, int TH>
+void launch_rb_tile_t(bool up, const TileArgs &t, cudaStream_t st)
+{
+    dim3 g((t.nx + TW - 1) / TW, (t.ny + TH - 1) / TH, 1);
+    if (up) mg_up_rb_kernel<TW, TH><<<g, kTileThreads, RbCfg<TW, TH, 4>::kSmemUp, st>>>(t);
+    else mg_down_rb_kernel<TW, TH><<<g, kTileThreads, RbCfg<TW, TH, 6>::kSmemDown, st>>>(t);
+}
+void launch_rb_tile(int choice, bool up, const TileArgs &t, cudaStream_t st)
+{
+    switch (choice) {
+    default:
+    case 0: launch_rb_tile_t<64, 32>(up, t, st); break;
+    case 1: launch_rb_tile_t<64, 16>(up, t, st); break;
+    case 2: launch_rb_tile_t<32, 32>(up, t, st); break;
+    case 3: launch_rb_tile_t<128, 16>(up, t, st); break;
+    case 4: launch_rb_tile_t<128, 32>(up, t, st); break;
+    }
+}
+template <int TW, int TH>
+cudaError_t rb_tile_set_attr_t()
+{
+    cudaError_t e = cudaFuncSetAttribute(mg_down_rb_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)RbCfg<TW, TH, 6>::kSmemDown);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mg_up_rb_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RbCfg<TW, TH, 4>::kSmemUp);
+}
+cudaError_t rb_tile_set_attr(int choice)
+{
+    switch (choice) {
+    default:
+    case 0: return rb_tile_set_attr_t<64, 32>();
+    case 1: return rb_tile_set_attr_t<64, 16>();
+    case 2: return rb_tile_set_attr_t<32, 32>();
+    case 3: return rb_tile_set_attr_t<128, 16>();
+    case 4: return rb_tile_set_attr_t<128, 32>();
+    }
+}
+
+// fused level kernels exist for Jacobi + injection (variant A) and red-black Gauss-Seidel + full weighting (variant B)
+inline bool fused_variant_a(const b2s_mg_config &c)
+{
+    return c.fuse_sweeps && c.smoother == B2S_SMOOTH_JACOBI && c.restriction == B2S_RESTRICT_INJECT;
+}
+inline bool fused_variant_b(const b2s_mg_config &c)
+{
+    return c.fuse_sweeps && c.smoother == B2S_SMOOTH_RBGS && c.restriction == B2S_RESTRICT_FW;
+}
+
 int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count);
 int cg_global(double *x_in, const double *b, double *work, double hx, double hy, double c, double tol, int nmax, int nx, int ny,
               cudaStream_t st, double *ss_out, int *iters_out, long long *count);
@@ -152,7 +203,8 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         }
     };
     const int fs = h->coarse_global ? h->nlev - 1 : h->first_smem;
-    const bool fused = c.fuse_sweeps && !rb && c.restriction == B2S_RESTRICT_INJECT;
+    const bool fused_b = fused_variant_b(c);
+    const bool fused = fused_variant_a(c) || fused_b;
     auto tile_args = [&](int l) {
         TileArgs t = {};
         t.cp = cp; t.level = l; t.rhs = h->rhs[l]; t.nx = h->nx[l]; t.ny = h->ny[l]; t.nxc = h->nx[l + 1]; t.nyc = h->ny[l + 1];
@@ -160,6 +212,11 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         return t;
     };
     const int tile_choice = h->tile_choice;
+    // variant-B tile shape: 32x32 on the latency-bound (L2-resident) levels, 64x32 (less halo redundancy) above -- measured
+    auto rb_choice = [&](int l) {
+        if (h->rb_tile_choice >= 0) return h->rb_tile_choice;
+        return (size_t)h->nx[l] * h->ny[l] > 1500000 ? 0 : 2;
+    };
     // downward leg on the global-memory levels
     // fuse_sweeps: 1 = automatic (streaming kernels for large levels, where their lower instruction count wins; tile
     // kernels for levels <= ~1.5 M points, which are latency-bound and prefer 3 barriers to a 24-step pipeline),
@@ -212,7 +269,9 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = 0; l < fs && fused; ++l) {
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
-        if (use_streaming(l) && warp_kind) {
+        if (fused_b) {
+            launch_rb_tile(rb_choice(l), false, t, st);
+        } else if (use_streaming(l) && warp_kind) {
             const int ch = warp_rows(l);
             mg_down_warp_kernel<<<warp_grid(l, ch), 32, 0, st>>>(t, ch);
         } else if (use_streaming(l) && two_col) {
@@ -261,7 +320,9 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        if (use_streaming(l) && warp_kind) {
+        if (fused_b) {
+            launch_rb_tile(rb_choice(l), true, t, st);
+        } else if (use_streaming(l) && warp_kind) {
             const int ch = warp_rows(l);
             mg_up_warp_kernel<<<warp_grid(l, ch), 32, 0, st>>>(t, ch);
         } else if (use_streaming(l) && two_col) {
@@ -443,7 +504,8 @@ int set_call(b2s_mg *h, double *u, const double *f, double hgrid, double c, doub
     m.n_points = (double)h->nx[0] * h->ny[0];
     m.hist = h->hist_dev;
     const int fs = h->coarse_global ? h->nlev - 1 : h->first_smem;
-    m.rb_combine = (h->cfg.smoother == B2S_SMOOTH_RBGS && fs > 0) ? 1 : 0;
+    // unfused red-black sweeps deposit one sum per colour; the fused upward kernel sums both colours itself
+    m.rb_combine = (h->cfg.smoother == B2S_SMOOTH_RBGS && fs > 0 && !fused_variant_b(h->cfg)) ? 1 : 0;
     m.pad = 0;
     B2S_CUDA(cudaMemcpyAsync(h->call_dev, h->call_pin, sizeof(MGCall), cudaMemcpyHostToDevice, h->stream));
     return B2S_OK;
@@ -608,6 +670,11 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         h->tile_choice = (e && *e) ? atoi(e) : 0;
         if (h->tile_choice < 0 || h->tile_choice > 3) h->tile_choice = 0;
         MG_CUDA(tile_set_attr(h->tile_choice));
+        const char *e6 = getenv("B2S_MG_RB_TILE");
+        h->rb_tile_choice = (e6 && *e6) ? atoi(e6) : -1;  // -1: per level (rb_choice)
+        if (h->rb_tile_choice < -1 || h->rb_tile_choice > 4) h->rb_tile_choice = -1;
+        if (h->rb_tile_choice >= 0) MG_CUDA(rb_tile_set_attr(h->rb_tile_choice));
+        else { MG_CUDA(rb_tile_set_attr(0)); MG_CUDA(rb_tile_set_attr(2)); }
         MG_CUDA(cudaFuncSetAttribute(mg_down_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemDown));
         MG_CUDA(cudaFuncSetAttribute(mg_up_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemUp));
         const char *e2 = getenv("B2S_MG_CH");

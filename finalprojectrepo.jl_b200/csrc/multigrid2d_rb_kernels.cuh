@@ -1,0 +1,280 @@
+// multigrid2d_rb_kernels.cuh -- variant B of hot path 2 (red-black Gauss-Seidel smoother + full-weighting restriction),
+// temporally blocked: one kernel per level for the downward leg and one for the upward leg, like the variant-A tile
+// kernels of multigrid2d_kernels.cuh.
+//
+// The split red/black layout lives where the sweeps happen -- in SHARED MEMORY. The arrays in HBM keep the caller's
+// natural column-major layout (a Julia CuArray can be passed as it is) and are read once and written once per leg with
+// fully coalesced accesses; while a tile is staged, every element is routed to one of two per-colour planes
+// (red: i+j even, black: i+j odd; element (c, r) of the staged window -> plane[(c+r)&1][r][c>>1]). A half sweep then
+// reads and writes unit-stride runs of one plane and unit-stride runs of the other (no 2-way bank conflicts, which a
+// natural layout would cost every half sweep). The right-hand side is split the same way; after the pre-smoothing its
+// planes are overwritten in place by the residual (res[p] needs rhs[p] only), from which the full-weighting stencil is
+// gathered.
+//
+//   mg_down_rb_kernel:  u_s = BR(BR(u)) (B = black, R = red half sweep, red first) ; rc = FW(residual(u_s)) (+ Neumann) ;
+//                       ec = 0                                            [reads u, rhs; writes u_s, rc, ec]
+//   mg_up_rb_kernel:    u = BR(BR(u_s - P(ec))) ; sum of the pre-update res^2 of the last red + black half sweeps
+//                                                                         [reads u_s, rhs, ec; writes u]
+// Semantics: iteration_2DPoisson_gs! (scripts-part2/multigrid.jl:269-297) restricted to one colour per half sweep
+// (alpha = 1, residual written with "/ h^2" as there), residual_2DPoisson! (:173-188), the V-cycle order of
+// Vcycle_2DPoisson! (:121-143). Every point value is produced by exactly the arithmetic of the unfused kernels
+// (mg_rbgs_kernel, mg_restrict_kernel, mg_prolong_kernel); halo points are recomputed redundantly by neighbouring
+// blocks (the halo shrinks by one per half sweep), so results are bit-identical to the unfused path and to the oracle.
+#pragma once
+#include "multigrid2d_kernels.cuh"
+
+namespace b2s {
+
+template <int TW, int TH, int HALO>
+struct RbCfg {
+    static constexpr int kW = TW + 2 * HALO;     // staged columns (even)
+    static constexpr int kRows = TH + 2 * HALO;  // staged rows
+    static constexpr int kP2 = kW / 2;           // row pitch of one colour plane
+    static constexpr int kPlane = kRows * kP2 + 4;  // +4: planes start 32 bytes apart in bank space
+    static constexpr int kCW = TW / 2 + 5, kCH = TH / 2 + 5;  // coarse window of the upward kernel (HALO = 4)
+    static constexpr size_t kSmemDown = (size_t)4 * kPlane * sizeof(double);
+    static constexpr size_t kSmemUp = ((size_t)4 * kPlane + (size_t)kCW * kCH) * sizeof(double);
+};
+
+struct RbCoef {
+    double C, h2, w, inv_h2;  // inv_h2: exact reciprocal when h^2 is a power of two (DivH2), unused otherwise
+};
+__device__ __forceinline__ RbCoef make_rb_coef(double h, double c)
+{
+    RbCoef k;
+    k.C = 4.0 + c * (h * h);
+    k.h2 = h * h;
+    k.w = 1.0 * ((h * h) / (4.0 + c * (h * h)));
+    k.inv_h2 = make_div_h2(k.h2).inv;
+    return k;
+}
+
+// Stage a window of a natural-layout global array into the two colour planes (asynchronous 8-byte copies; elements
+// outside the domain are zero-filled). (gx0, gy0) = global coordinates of window element (0,0); gx0 + gy0 is even, so
+// the local parity (c + r) & 1 is the global colour. Elements outside [c0, c1) x [r0, r1) are skipped.
+template <int kW, int kRows, int kP2>
+__device__ __forceinline__ void rb_stage(double *__restrict__ red, double *__restrict__ blk, const double *__restrict__ g, int gx0,
+                                         int gy0, int nx, int ny, int c0, int c1, int r0, int r1)
+{
+    for (int idx = threadIdx.x; idx < kW * kRows; idx += kTileThreads) {
+        const int r = idx / kW, c = idx - r * kW;
+        if (c < c0 || c >= c1 || r < r0 || r >= r1) continue;
+        const int i = gx0 + c, j = gy0 + r;
+        const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
+        double *dst = (((c + r) & 1) ? blk : red) + r * kP2 + (c >> 1);
+        cp_async8(dst, g + (in ? (size_t)i + (size_t)nx * j : 0), in);
+    }
+}
+
+// One half sweep of colour X (0 = red) over the window [HALO-K, HALO+TW+K) x [HALO-K, HALO+TH+K) of the staged tile,
+// in place in the colour planes. NORM: accumulate the pre-update res^2 of the points inside the tile proper.
+// DIV: true = divide by h^2 as written in the reference, false = multiply by the exact reciprocal (same bits, DivH2).
+template <int TW, int TH, int HALO, int K, bool CHECKED, bool NORM, bool DIV>
+__device__ __forceinline__ double rb_half_sweep(double *__restrict__ own, const double *__restrict__ oth,
+                                                const double *__restrict__ F, int X, int gx0, int gy0, int nx, int ny,
+                                                const RbCoef &k)
+{
+    using Cf = RbCfg<TW, TH, HALO>;
+    constexpr int kP2 = Cf::kP2;
+    constexpr int w0 = HALO - K, W = TW + 2 * K, H = TH + 2 * K;
+    constexpr int HW = (W + 1) / 2;
+    double acc = 0.0;
+    for (int idx = threadIdx.x; idx < H * HW; idx += kTileThreads) {
+        const int rr = idx / HW, kk = idx - rr * HW;
+        const int r = w0 + rr;
+        const int par = (r + X) & 1;                      // parity of the columns of colour X in this row
+        const int c = w0 + ((w0 ^ par) & 1) + 2 * kk;     // kk-th column >= w0 of that parity
+        if (c >= w0 + W) continue;
+        if (CHECKED) {
+            const int i = gx0 + c, j = gy0 + r;
+            if (i < 1 || j < 1 || i > nx - 2 || j > ny - 2) continue;
+        }
+        const int s = r * kP2 + (c >> 1);
+        const double v = own[s];
+        // (uE + uW + uN + uS - C u) / h^2 - f     multigrid.jl:279-283; E/W neighbours sit at s+par / s-1+par of the
+        // other plane, N/S neighbours at the same index of the rows above and below
+        const double t = oth[s + par] + oth[s - 1 + par] + oth[s + kP2] + oth[s - kP2] - k.C * v;
+        const double res = (DIV ? t / k.h2 : t * k.inv_h2) - F[s];
+        own[s] = v + k.w * res;
+        if (NORM) {
+            if (K == 0 || (c >= HALO && c < HALO + TW && r >= HALO && r < HALO + TH)) acc += res * res;
+        }
+    }
+    return acc;
+}
+
+// the four half sweeps of the downward leg (pre-smoothing: red, black, red, black; the valid window shrinks by one each)
+template <int TW, int TH, bool CHECKED, bool DIV>
+__device__ __forceinline__ void rb_down_sweeps(double *UR, double *UB, const double *FR, const double *FB, int gx0, int gy0, int nx,
+                                               int ny, const RbCoef &k)
+{
+    rb_half_sweep<TW, TH, 6, 5, CHECKED, false, DIV>(UR, UB, FR, 0, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    rb_half_sweep<TW, TH, 6, 4, CHECKED, false, DIV>(UB, UR, FB, 1, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    rb_half_sweep<TW, TH, 6, 3, CHECKED, false, DIV>(UR, UB, FR, 0, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    rb_half_sweep<TW, TH, 6, 2, CHECKED, false, DIV>(UB, UR, FB, 1, gx0, gy0, nx, ny, k);
+}
+// the four half sweeps of the upward leg; returns this thread's share of the last full sweep's pre-update res^2
+template <int TW, int TH, bool CHECKED, bool DIV>
+__device__ __forceinline__ double rb_up_sweeps(double *UR, double *UB, const double *FR, const double *FB, int gx0, int gy0, int nx,
+                                               int ny, const RbCoef &k)
+{
+    rb_half_sweep<TW, TH, 4, 3, CHECKED, false, DIV>(UR, UB, FR, 0, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    rb_half_sweep<TW, TH, 4, 2, CHECKED, false, DIV>(UB, UR, FB, 1, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    double acc = rb_half_sweep<TW, TH, 4, 1, CHECKED, true, DIV>(UR, UB, FR, 0, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    acc += rb_half_sweep<TW, TH, 4, 0, CHECKED, true, DIV>(UB, UR, FB, 1, gx0, gy0, nx, ny, k);
+    return acc;
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(kTileThreads) mg_down_rb_kernel(const TileArgs a)
+{
+    constexpr int HALO = 6;
+    using Cf = RbCfg<TW, TH, HALO>;
+    constexpr int kW = Cf::kW, kRows = Cf::kRows, kP2 = Cf::kP2, kPlane = Cf::kPlane;
+    extern __shared__ __align__(16) double tsm[];
+    double *UR = tsm, *UB = tsm + kPlane, *FR = tsm + 2 * kPlane, *FB = tsm + 3 * kPlane;
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double *u = a.u_in, *rhs = a.rhs;
+    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
+    const int apply_bcs = cp->apply_bcs;
+    const double hl = level_h(cp, a.level);
+    const RbCoef k = make_rb_coef(hl, cp->c);
+    const Coef kr = make_coef(hl, cp->c, 1.0);
+    const int nx = a.nx, ny = a.ny;
+    const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
+    const int gx0 = X0 - HALO, gy0 = Y0 - HALO;
+    rb_stage<kW, kRows, kP2>(UR, UB, u, gx0, gy0, nx, ny, 0, kW, 0, kRows);
+    rb_stage<kW, kRows, kP2>(FR, FB, rhs, gx0, gy0, nx, ny, 1, kW - 1, 1, kRows - 1);
+    cp_async_wait_all();
+    __syncthreads();
+    // block-uniform: does the widest window (halo 5) stay strictly inside the domain?
+    const bool inner = X0 - 5 >= 1 && Y0 - 5 >= 1 && X0 + TW + 4 <= nx - 2 && Y0 + TH + 4 <= ny - 2;
+    const bool div = !make_div_h2(k.h2).exact;
+    if (inner && !div) rb_down_sweeps<TW, TH, false, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    else if (inner) rb_down_sweeps<TW, TH, false, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    else if (!div) rb_down_sweeps<TW, TH, true, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    else rb_down_sweeps<TW, TH, true, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    // smoothed u out (natural layout, coalesced)
+    for (int idx = threadIdx.x; idx < TW * TH; idx += kTileThreads) {
+        const int r = idx / TW, c = idx - r * TW;
+        const int i = X0 + c, j = Y0 + r;
+        if (i >= nx || j >= ny) continue;
+        const int lc = c + HALO, lr = r + HALO;
+        a.u_out[(size_t)i + (size_t)nx * j] = (((lc + lr) & 1) ? UB : UR)[lr * kP2 + (lc >> 1)];
+    }
+    // residual of the smoothed u on tile+1, in place of the right-hand side (multigrid.jl:173-188); interior points only
+    // -- the full-weighting stencil of an interior coarse point never reaches the fine frame
+    {
+        constexpr int W = TW + 2, H = TH + 2, w0 = HALO - 1;
+        for (int idx = threadIdx.x; idx < W * H; idx += kTileThreads) {
+            const int rr = idx / W, cc = idx - rr * W;
+            const int c = w0 + cc, r = w0 + rr;
+            const int i = gx0 + c, j = gy0 + r;
+            if (i < 1 || j < 1 || i > nx - 2 || j > ny - 2) continue;
+            const int par = (c + r) & 1, cpar = c & 1;
+            const double *own = par ? UB : UR, *oth = par ? UR : UB;
+            double *F = par ? FB : FR;
+            const int s = r * kP2 + (c >> 1);
+            F[s] = ((oth[s + cpar] + oth[s - 1 + cpar] + oth[s + kP2] + oth[s - kP2] - kr.C * own[s]) * kr._h2 - F[s]);
+        }
+    }
+    __syncthreads();
+    // coarse rhs = full weighting of the residual (+ Neumann copies), coarse unknown = 0
+    const int nxc = a.nxc, nyc = a.nyc;
+    for (int idx = threadIdx.x; idx < (TW / 2) * (TH / 2); idx += kTileThreads) {
+        const int rr = idx / (TW / 2), cc = idx - rr * (TW / 2);
+        const int I = X0 / 2 + cc, J = Y0 / 2 + rr;
+        if (I >= nxc || J >= nyc) continue;
+        const size_t pc = (size_t)I + (size_t)nxc * J;
+        a.ec[pc] = 0.0;
+        const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
+        if (interior) {
+            // fine point (2I, 2J): local (even, even) -> red plane; its x neighbours are black at m-1, m; the diagonal
+            // neighbours are red at m-1, m of the rows below and above
+            const int s = (2 * rr + HALO) * kP2 + (cc + HALO / 2);
+            const double corners = (FR[s - kP2 - 1] + FR[s - kP2]) + (FR[s + kP2 - 1] + FR[s + kP2]);
+            const double edges = (FB[s - 1] + FB[s]) + (FB[s - kP2] + FB[s + kP2]);
+            const double v = ((corners + 2.0 * edges) + 4.0 * FR[s]) * 0.0625;
+            a.rc[pc] = v;
+            if (apply_bcs) {  // coarse[0,:] = coarse[1,:] ; coarse[nxc-1,:] = coarse[nxc-2,:]
+                if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                if (I == nxc - 2) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+            }
+        } else if (!(apply_bcs && (I == 0 || I == nxc - 1) && J >= 1 && J <= nyc - 2)) {
+            a.rc[pc] = 0.0;
+        }
+    }
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a)
+{
+    constexpr int HALO = 4;
+    using Cf = RbCfg<TW, TH, HALO>;
+    constexpr int kW = Cf::kW, kRows = Cf::kRows, kP2 = Cf::kP2, kPlane = Cf::kPlane, kCW = Cf::kCW, kCH = Cf::kCH;
+    extern __shared__ __align__(16) double tsm[];
+    __shared__ double red[32];
+    double *UR = tsm, *UB = tsm + kPlane, *FR = tsm + 2 * kPlane, *FB = tsm + 3 * kPlane, *Cw = tsm + 4 * kPlane;
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double *rhs = a.rhs;
+    double *out = a.u_out;
+    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
+    const int apply_bcs = cp->apply_bcs;
+    const RbCoef k = make_rb_coef(level_h(cp, a.level), cp->c);
+    const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
+    const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
+    const int gx0 = X0 - HALO, gy0 = Y0 - HALO;
+    const int cx0 = X0 / 2 - 2, cy0 = Y0 / 2 - 2;
+    rb_stage<kW, kRows, kP2>(UR, UB, a.u_in, gx0, gy0, nx, ny, 0, kW, 0, kRows);
+    rb_stage<kW, kRows, kP2>(FR, FB, rhs, gx0, gy0, nx, ny, 1, kW - 1, 1, kRows - 1);
+    for (int idx = threadIdx.x; idx < kCW * kCH; idx += kTileThreads) {
+        const int r = idx / kCW, c = idx - r * kCW;
+        const int I = cx0 + c, J = cy0 + r;
+        const bool in = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;  // the boundary ring counts as 0
+        cp_async8(Cw + idx, a.ec + (in ? (size_t)I + (size_t)nxc * J : 0), in);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // u_f .= u_f - corr_f on tile+4 (multigrid.jl:136-139)
+    for (int idx = threadIdx.x; idx < kW * kRows; idx += kTileThreads) {
+        const int r = idx / kW, c = idx - r * kW;
+        const int i = gx0 + c, j = gy0 + r;
+        if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
+        double *p = (((c + r) & 1) ? UB : UR) + r * kP2 + (c >> 1);
+        *p = *p - prolong_from_window<kCW>(Cw, cx0, cy0, nx, i, j, apply_bcs);
+    }
+    __syncthreads();
+    const bool inner = X0 - 3 >= 1 && Y0 - 3 >= 1 && X0 + TW + 2 <= nx - 2 && Y0 + TH + 2 <= ny - 2;
+    const bool div = !make_div_h2(k.h2).exact;
+    double acc;
+    if (inner && !div) acc = rb_up_sweeps<TW, TH, false, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    else if (inner) acc = rb_up_sweeps<TW, TH, false, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    else if (!div) acc = rb_up_sweeps<TW, TH, true, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    else acc = rb_up_sweeps<TW, TH, true, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TW * TH; idx += kTileThreads) {
+        const int r = idx / TW, c = idx - r * TW;
+        const int i = X0 + c, j = Y0 + r;
+        if (i >= nx || j >= ny) continue;
+        const int lc = c + HALO, lr = r + HALO;
+        out[(size_t)i + (size_t)nx * j] = (((lc + lr) & 1) ? UB : UR)[lr * kP2 + (lc >> 1)];
+    }
+    if (a.want_norm) {
+        const int nblocks = gridDim.x * gridDim.y;
+        const int bl = blockIdx.x + gridDim.x * blockIdx.y;
+        const double bsum = block_sum(acc, red);
+        double total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+    }
+}
+
+}  // namespace b2s

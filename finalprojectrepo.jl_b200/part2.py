@@ -386,7 +386,7 @@ def mg_fused_min_bytes(nx, ny, coarse_solve_size=5):
     return mg_algorithmic_bytes(nx, ny, coarse_solve_size) / 132.0 * 54.0
 
 
-def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycles=50, seed=1):
+def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycles=50, seed=1, opt=None):
     """Config #2 (multigrid_bench.jl shape): x = 0, b ~ U[0,1) on all entries, c = 0, tol 1e-6; DoF/s per V-cycle with
     fields resident on the device (CUDA events inside the library), plus the whole-solve time and cycle count."""
     torch = _torch()
@@ -394,7 +394,7 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
     for n in sizes:
         h = 1.0 / (n - 1)
         b = to_device(np.random.default_rng(seed).random((n, n)), device)
-        hd = MGHandle(n, n, MGOpt(), device)
+        hd = MGHandle(n, n, opt if opt is not None else MGOpt(), device)
         x = zeros(n, n, device)
         hd.cycles(x, b, h, 0.0, 1e-6, 3)  # warm-up (graph instantiation)
         x.zero_()

@@ -113,7 +113,8 @@ CONFIGS = [
     dict(coarse_solve_size=9),
     dict(coarse_solver=1),                              # CG coarse solver
     dict(coarse_solve_size=9, coarse_solver=1, use_graph=False),
-    dict(smoother=1, restriction=1),                    # variant B: RB-GS + full weighting
+    dict(smoother=1, restriction=1),                    # variant B: RB-GS + full weighting (fused tile kernels)
+    dict(smoother=1, restriction=1, fuse_sweeps=False), # variant B, one kernel per half sweep / transfer operator
     dict(smoother=1, restriction=1, use_graph=False, smem_levels=False),
 ]
 
@@ -145,6 +146,26 @@ def test_vcycle_matches_oracle(p2, oracle, cfg, shape, c, bcs):
             assert np.max(np.abs(got - uo)) <= 1e-11 * np.max(np.abs(uo)), cyc
         else:
             assert np.array_equal(got, uo), cyc
+    hd.close()
+
+
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "unfused"])
+@pytest.mark.parametrize("shape,h,c,bcs", [((257, 129), 0.013, 0.0, False), ((129, 321), 1.0 / 96, 77.7, True),
+                                           ((513, 257), 2.0 ** -9, 0.0, True)])
+def test_variant_b_vcycle_general_h(p2, oracle, fuse, shape, h, c, bcs):
+    """Variant B with grid spacings whose square is not a power of two (the kernels then divide by h^2 as the reference's
+    Gauss-Seidel does, multigrid.jl:279-283) and with one that is (exact-reciprocal path); ragged tile edges."""
+    nx, ny = shape
+    opt_o = oracle.MGOpt(smoother=1, restriction=1)
+    u, f = rnd(shape, 31), rnd(shape, 32)
+    hd = p2.preallocate_buffers(nx, ny, p2.MGOpt(smoother=1, restriction=1, fuse_sweeps=fuse))
+    du, df = p2.to_device(u), p2.to_device(f)
+    uo = u.copy(order="F")
+    for cyc in range(2):
+        r_o = oracle.vcycle2d(uo, f, h, c, 1e-6, bcs, opt_o)
+        r_g = hd.vcycle(du, df, h, c, 1e-6, bcs)
+        assert abs(r_g - r_o) <= 1e-11 * r_o, cyc
+        assert np.array_equal(p2.to_host(du), uo), cyc
     hd.close()
 
 
