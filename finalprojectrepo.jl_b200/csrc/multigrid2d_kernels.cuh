@@ -1831,6 +1831,130 @@ __device__ __forceinline__ double warp_coarsest_jacobi(double *u, const double *
     return tot;
 }
 
+// Coarsest solve of a grid with <= 32 points (5x5, the default coarse_solve_size) in the registers of one warp: one point
+// per lane, neighbours by shuffle. Measured on the B200 (scripts/microbench): FP64 add/mul latency 8 cycles, a 64-bit
+// shuffle 25, so one Jacobi sweep is a ~120-cycle dependent chain (4 shuffles + 8 FP64 operations + select) that nothing
+// can shorten -- but everything else can be taken off it. The reference's exit test (res_rms < tol_rhs after every
+// sweep, multigrid.jl:150-156) needs a warp-wide sum per sweep: sweeps therefore run speculatively in batches of 8, each
+// sweep drops its per-lane res^2 and its state into shared memory (stores nobody waits for), and once per batch all 32
+// lanes reduce the 8 sums together (4 lanes per sweep: 8 loads, a 3-level add tree, 2 shuffle levels, one ballot). If
+// sweep j of the batch is the first to pass the test, the state after sweep j is simply read back. The arithmetic per
+// sweep is that of the sequential loop, so solution and sweep count are identical to it.
+// RB: red-black Gauss-Seidel (variant B) instead of damped Jacobi: two half steps per sweep.
+template <bool RB>
+struct RegSweep {
+    double f, C, s2, kw;   // s2: 1/h^2 (Jacobi) or the exact reciprocal / h^2 itself (RB, see DivH2)
+    bool interior, red, exact;
+    int up, dn;
+    struct Nb { double e, w, n, s; };
+    __device__ __forceinline__ Nb gather(double v) const
+    {
+        Nb q;
+        q.e = __shfl_down_sync(0xffffffffu, v, 1); q.w = __shfl_up_sync(0xffffffffu, v, 1);
+        q.n = __shfl_sync(0xffffffffu, v, up); q.s = __shfl_sync(0xffffffffu, v, dn);
+        return q;
+    }
+    __device__ __forceinline__ double update(const Nb &q, double v, bool active, double &acc) const
+    {
+        const double t = q.e + q.w + q.n + q.s - C * v;
+        double r;
+        if (RB) r = (exact ? t * s2 : t / s2) - f;   // (...) / h^2 - f   multigrid.jl:279-283
+        else r = (t * s2 - f);                       // (...) * _h2 - f   multigrid.jl:183-187
+        const double vn = v + kw * r;
+        if (active) acc = r * r;
+        return active ? vn : v;
+    }
+    __device__ __forceinline__ double sweep(double v, double &acc) const
+    {
+        acc = 0.0;
+        if (!RB) return update(gather(v), v, interior, acc);
+        v = update(gather(v), v, interior && red, acc);
+        return update(gather(v), v, interior && !red, acc);
+    }
+};
+
+#ifdef B2S_COARSEST_STAMPS
+__device__ long long g_stamps[64];
+#endif
+template <bool RB>
+__device__ __noinline__ double warp_coarsest_reg(double *u, const double *rhs, int nx, int ny, double h, double c, double sstar,
+                                                 int iters, int *sweeps_out)
+{
+    __shared__ double accbuf[8][32], vbuf[8][32];
+#ifdef B2S_COARSEST_STAMPS
+    __shared__ long long s_stamps[64];
+    int nst = 0;
+#endif
+    const int lane = threadIdx.x & 31, n = nx * ny;
+    const bool valid = lane < n;
+    const int j = lane / nx, i = lane - j * nx;
+    RegSweep<RB> sw;
+    sw.interior = valid && i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
+    sw.red = ((i + j) & 1) == 0;
+    sw.up = lane + nx; sw.dn = lane - nx;
+    sw.f = valid ? rhs[lane] : 0.0;
+    sw.exact = true;
+    if (RB) {
+        const DivH2 dh = make_div_h2(h * h);
+        sw.C = 4.0 + c * (h * h); sw.kw = 1.0 * ((h * h) / sw.C);
+        sw.exact = dh.exact; sw.s2 = dh.exact ? dh.inv : dh.h2;
+    } else {
+        const Coef k = make_coef(h, c, 4.0 / 5.0);
+        sw.C = k.C; sw.s2 = k._h2; sw.kw = k.w;
+    }
+    double v = valid ? u[lane] : 0.0;
+    const int rb = lane >> 2, rp = (lane & 3) * 8;  // reduction: lanes 4b..4b+3 sum sweep b, 8 lanes' worth each
+    double tot = 0.0;
+    int s = 0;
+    for (;;) {
+        const int nb = min(8, iters - s);
+#ifdef B2S_COARSEST_STAMPS
+        if (nst < 60) s_stamps[nst++] = clock64();
+#endif
+        if (nb == 8) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                double a;
+                v = sw.sweep(v, a);
+                accbuf[b][lane] = a;
+                vbuf[b][lane] = v;
+            }
+        } else {
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                double a;
+                v = sw.sweep(v, a);
+                accbuf[b][lane] = a;
+                vbuf[b][lane] = v;
+            }
+        }
+#ifdef B2S_COARSEST_STAMPS
+        if (nst < 60) s_stamps[nst++] = clock64();
+#endif
+        __syncwarp();
+        const double *q = &accbuf[rb][rp];
+        double t = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        const unsigned ok = __ballot_sync(0xffffffffu, rb < nb && t < sstar);
+        __syncwarp();
+        int hit = ok ? ((__ffs(ok) - 1) >> 2) : -1;  // first sweep of the batch that passes res_rms < tol_rhs
+        if (hit < 0 && s + nb < iters) { s += nb; continue; }
+        if (hit < 0) hit = nb - 1;  // the cap 20*coarse_solve_size ends the loop
+        tot = __shfl_sync(0xffffffffu, t, 4 * hit);
+        v = vbuf[hit][lane];  // state after the last counted sweep
+        s += hit + 1;
+        break;
+    }
+    if (valid) u[lane] = v;
+    __syncwarp();
+#ifdef B2S_COARSEST_STAMPS
+    if (lane == 0) for (int q = 0; q < 64; ++q) g_stamps[q] = q < nst ? s_stamps[q] : 0;
+#endif
+    if (sweeps_out != nullptr && lane == 0) *sweeps_out = s;
+    return tot;
+}
+
 // Coarsest-level solve (multigrid.jl:145-167). u in place; tmp = scratch of the level; work = CG scratch.
 template <class G>
 __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const double *rhs, double *tmp, double *work, int nx,
@@ -1844,6 +1968,10 @@ __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const doubl
         const double tol_rhs = tol * sqrt(sm_sumsq(g, rhs, n) / N);
         const double sstar = exit_threshold(tol_rhs, N);  // res_rms < tol_rhs  <=>  ss < sstar
         const Coef k = make_coef(h, c, 4.0 / 5.0);
+        if (g.size() == 32 && n <= 32 && nx >= 3) {  // register-resident solve (shuffles wrap correctly only for nx >= 2)
+            if (a.smoother == B2S_SMOOTH_RBGS) return warp_coarsest_reg<true>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
+            return warp_coarsest_reg<false>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
+        }
         if (a.smoother == B2S_SMOOTH_JACOBI && g.size() == 32 && n <= 128) {
             if (n <= 32) return warp_coarsest_jacobi<1>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);
             if (n <= 64) return warp_coarsest_jacobi<2>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);
