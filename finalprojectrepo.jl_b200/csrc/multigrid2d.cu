@@ -31,6 +31,11 @@ inline dim3 sweep_grid(int nx, int ny, int rows) { return dim3((nx + kMGBX - 1) 
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 constexpr size_t kCoarseSmemLimit = 200 * 1024;
+inline size_t smem_level_max_points()
+{
+    const char *e = getenv("B2S_MG_SMEM_MAXPTS");
+    return (e && *e) ? (size_t)atoll(e) : (size_t)600;  // measured: 33^2 and 65^2 are faster as small-tile kernels
+}
 
 }  // namespace
 
@@ -54,7 +59,8 @@ struct b2s_mg {
     long long kernel_launches = 0;
     long long launches_per_cycle = 0;
     double last_ms = 0.0;
-    int tile_choice = 0;
+    int tile_choice = -1;
+    int tile_min_blocks = 400;
     int rb_tile_choice = -1;
     int stream_ch = 0;
     bool stream_warp = false;            // automatic mode: block-wide two-column streaming kernels (measured faster than the
@@ -86,8 +92,13 @@ void launch_tile(int choice, bool up, const TileArgs &t, cudaStream_t st)
     case 1: launch_tile_t<32, 32>(up, t, st); break;
     case 2: launch_tile_t<64, 32>(up, t, st); break;
     case 3: launch_tile_t<128, 16>(up, t, st); break;
+    case 4: launch_tile_t<32, 16>(up, t, st); break;
+    case 5: launch_tile_t<32, 8>(up, t, st); break;
+    case 6: launch_tile_t<16, 8>(up, t, st); break;
     }
 }
+constexpr int kTileChoices = 7;
+constexpr int kTileW[kTileChoices] = {64, 32, 64, 128, 32, 32, 16}, kTileH[kTileChoices] = {16, 32, 32, 16, 16, 8, 8};
 template <int TW, int TH>
 cudaError_t tile_set_attr_t()
 {
@@ -104,6 +115,9 @@ cudaError_t tile_set_attr(int choice)
     case 1: return tile_set_attr_t<32, 32>();
     case 2: return tile_set_attr_t<64, 32>();
     case 3: return tile_set_attr_t<128, 16>();
+    case 4: return tile_set_attr_t<32, 16>();
+    case 5: return tile_set_attr_t<32, 8>();
+    case 6: return tile_set_attr_t<16, 8>();
     }
 }
 
@@ -124,8 +138,13 @@ void launch_rb_tile(int choice, bool up, const TileArgs &t, cudaStream_t st)
     case 2: launch_rb_tile_t<32, 32>(up, t, st); break;
     case 3: launch_rb_tile_t<128, 16>(up, t, st); break;
     case 4: launch_rb_tile_t<128, 32>(up, t, st); break;
+    case 5: launch_rb_tile_t<32, 16>(up, t, st); break;
+    case 6: launch_rb_tile_t<16, 16>(up, t, st); break;
+    case 7: launch_rb_tile_t<16, 8>(up, t, st); break;
     }
 }
+constexpr int kRbTileChoices = 8;
+constexpr int kRbTileW[kRbTileChoices] = {64, 64, 32, 128, 128, 32, 16, 16}, kRbTileH[kRbTileChoices] = {32, 16, 32, 16, 32, 16, 16, 8};
 template <int TW, int TH>
 cudaError_t rb_tile_set_attr_t()
 {
@@ -143,6 +162,9 @@ cudaError_t rb_tile_set_attr(int choice)
     case 2: return rb_tile_set_attr_t<32, 32>();
     case 3: return rb_tile_set_attr_t<128, 16>();
     case 4: return rb_tile_set_attr_t<128, 32>();
+    case 5: return rb_tile_set_attr_t<32, 16>();
+    case 6: return rb_tile_set_attr_t<16, 16>();
+    case 7: return rb_tile_set_attr_t<16, 8>();
     }
 }
 
@@ -211,11 +233,30 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
         t.partials = h->partials; t.ticket = h->ticket; t.sumsq_out = h->sumsq_dev;
         return t;
     };
-    const int tile_choice = h->tile_choice;
+    // variant-A tile shape per level: the levels below ~0.3 M points are latency-bound chains of block-wide phases, so they
+    // get the largest tile that still yields >= tile_min_blocks blocks (more, smaller blocks = shorter per-block chains;
+    // the extra halo traffic stays in L2). B2S_MG_TILE pins one shape for every level.
+    auto tile_choice_for = [&](int l) {
+        if (h->tile_choice >= 0) return h->tile_choice;
+        const int order[4] = {0, 4, 5, 6};  // 64x16, 32x16, 32x8, 16x8
+        for (int k = 0; k < 4; ++k) {
+            const int c_ = order[k];
+            const long nb = (long)((h->nx[l] + kTileW[c_] - 1) / kTileW[c_]) * ((h->ny[l] + kTileH[c_] - 1) / kTileH[c_]);
+            if (nb >= h->tile_min_blocks) return c_;
+        }
+        return 6;
+    };
     // variant-B tile shape: 32x32 on the latency-bound (L2-resident) levels, 64x32 (less halo redundancy) above -- measured
     auto rb_choice = [&](int l) {
         if (h->rb_tile_choice >= 0) return h->rb_tile_choice;
-        return (size_t)h->nx[l] * h->ny[l] > 1500000 ? 0 : 2;
+        if ((size_t)h->nx[l] * h->ny[l] > 1500000) return 0;
+        const int order[4] = {2, 5, 6, 7};  // 32x32, 32x16, 16x16, 16x8
+        for (int k = 0; k < 4; ++k) {
+            const int c_ = order[k];
+            const long nb = (long)((h->nx[l] + kRbTileW[c_] - 1) / kRbTileW[c_]) * ((h->ny[l] + kRbTileH[c_] - 1) / kRbTileH[c_]);
+            if (nb >= h->tile_min_blocks) return c_;
+        }
+        return 7;
     };
     // downward leg on the global-memory levels
     // fuse_sweeps: 1 = automatic (streaming kernels for large levels, where their lower instruction count wins; tile
@@ -281,7 +322,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
             const int ch = stream_rows(l);
             mg_down_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
         } else {
-            launch_tile(tile_choice, false, t, st);
+            launch_tile(tile_choice_for(l), false, t, st);
         }
         ++n;
     }
@@ -332,7 +373,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
             const int ch = stream_rows(l);
             mg_up_stream_kernel<<<stream_grid(l, ch), kSNT, 0, st>>>(t, ch);
         } else {
-            launch_tile(tile_choice, true, t, st);
+            launch_tile(tile_choice_for(l), true, t, st);
         }
         ++n;
     }
@@ -602,6 +643,9 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
             const size_t add = 3 * (size_t)h->nx[l] * h->ny[l] * 8;
             if (bytes + add > kCoarseSmemLimit) break;
             if (!cfg->smem_levels && l < L - 1) break;
+            // levels above this size run faster as tile kernels spread over many SMs than inside the one-block kernel
+            if (l < L - 1 && (fused_variant_a(*cfg) || fused_variant_b(*cfg)) &&
+                (size_t)h->nx[l] * h->ny[l] > smem_level_max_points()) break;
             bytes += add;
             fs = l;
         }
@@ -667,14 +711,15 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
     MG_CUDA(cudaFuncSetAttribute(mg_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemLimit + 1024));
     {
         const char *e = getenv("B2S_MG_TILE");
-        h->tile_choice = (e && *e) ? atoi(e) : 0;
-        if (h->tile_choice < 0 || h->tile_choice > 3) h->tile_choice = 0;
-        MG_CUDA(tile_set_attr(h->tile_choice));
+        h->tile_choice = (e && *e) ? atoi(e) : -1;  // -1: per level (tile_choice_for)
+        if (h->tile_choice < -1 || h->tile_choice >= kTileChoices) h->tile_choice = -1;
+        for (int t_ = 0; t_ < kTileChoices; ++t_) MG_CUDA(tile_set_attr(t_));
+        const char *e7 = getenv("B2S_MG_TILE_MINBLOCKS");
+        if (e7 && *e7) h->tile_min_blocks = atoi(e7);
         const char *e6 = getenv("B2S_MG_RB_TILE");
         h->rb_tile_choice = (e6 && *e6) ? atoi(e6) : -1;  // -1: per level (rb_choice)
-        if (h->rb_tile_choice < -1 || h->rb_tile_choice > 4) h->rb_tile_choice = -1;
-        if (h->rb_tile_choice >= 0) MG_CUDA(rb_tile_set_attr(h->rb_tile_choice));
-        else { MG_CUDA(rb_tile_set_attr(0)); MG_CUDA(rb_tile_set_attr(2)); }
+        if (h->rb_tile_choice < -1 || h->rb_tile_choice >= kRbTileChoices) h->rb_tile_choice = -1;
+        for (int t_ = 0; t_ < kRbTileChoices; ++t_) MG_CUDA(rb_tile_set_attr(t_));
         MG_CUDA(cudaFuncSetAttribute(mg_down_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemDown));
         MG_CUDA(cudaFuncSetAttribute(mg_up_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2SmemUp));
         const char *e2 = getenv("B2S_MG_CH");
