@@ -31,6 +31,8 @@ inline dim3 sweep_grid(int nx, int ny, int rows) { return dim3((nx + kMGBX - 1) 
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 constexpr size_t kCoarseSmemLimit = 200 * 1024;
+// device / pinned layout of a call: [MGCall][LevelCoef x kMaxLevels]; the pinned copy is followed by the read-back MGCall
+constexpr size_t kCallBlockBytes = sizeof(MGCall) + kMaxLevels * sizeof(LevelCoef);
 inline size_t smem_level_max_points()
 {
     const char *e = getenv("B2S_MG_SMEM_MAXPTS");
@@ -46,7 +48,7 @@ struct b2s_mg {
     double *u[kMaxLevels] = {}, *rhs[kMaxLevels] = {}, *tmp[kMaxLevels] = {};  // u/rhs for l >= 1, tmp for all
     int first_smem = 0;  // first level handled by the collapsed kernel
     size_t coarse_smem = 0;
-    MGCall *call_dev = nullptr, *call_pin = nullptr;  // call_pin[0]: upload staging, call_pin[1]: download staging
+    MGCall *call_dev = nullptr, *call_pin = nullptr;  // call_pin: upload staging [MGCall][LevelCoef...], then the read-back MGCall
     double *hist_dev = nullptr, *hist_pin = nullptr;
     double *sumsq_dev = nullptr;  // [0] last sweep, [1] f, [2],[3] rbgs colours
     double *sumsq_pin = nullptr;
@@ -535,6 +537,8 @@ int launch_cycle(b2s_mg *h)
     return B2S_OK;
 }
 
+inline MGCall *call_back(b2s_mg *h) { return reinterpret_cast<MGCall *>(reinterpret_cast<char *>(h->call_pin) + kCallBlockBytes); }
+
 int set_call(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int apply_bcs, int bc_before,
              int niters, int check)
 {
@@ -548,7 +552,28 @@ int set_call(b2s_mg *h, double *u, const double *f, double hgrid, double c, doub
     // unfused red-black sweeps deposit one sum per colour; the fused upward kernel sums both colours itself
     m.rb_combine = (h->cfg.smoother == B2S_SMOOTH_RBGS && fs > 0 && !fused_variant_b(h->cfg)) ? 1 : 0;
     m.pad = 0;
-    B2S_CUDA(cudaMemcpyAsync(h->call_dev, h->call_pin, sizeof(MGCall), cudaMemcpyHostToDevice, h->stream));
+    // per-level constants, in the arithmetic of make_coef / make_rb_coef / make_div_h2 (this file is compiled without
+    // floating-point contraction on the host side as well)
+    LevelCoef *lev = reinterpret_cast<LevelCoef *>(h->call_pin + 1);
+    m.lev = reinterpret_cast<const LevelCoef *>(h->call_dev + 1);
+    double hl = hgrid;
+    for (int l = 0; l < h->nlev; ++l) {
+        LevelCoef &L = lev[l];
+        L.h = hl;
+        L.C = 4.0 + c * (hl * hl);
+        L._h2 = 1 / (hl * hl);
+        L.wJ = (4.0 / 5.0) * ((hl * hl) / (4.0 + c * (hl * hl)));
+        L.h2 = hl * hl;
+        L.wGS = 1.0 * ((hl * hl) / (4.0 + c * (hl * hl)));
+        unsigned long long b;
+        memcpy(&b, &L.h2, sizeof b);
+        const int e = (int)((b >> 52) & 0x7ff);
+        L.exact = ((long long)b > 0 && (b & 0x000fffffffffffffULL) == 0 && e >= 2 && e <= 2044) ? 1 : 0;
+        L.inv_h2 = L.exact ? 1.0 / L.h2 : 0.0;
+        L.pad = 0;
+        hl = hl * 2;
+    }
+    B2S_CUDA(cudaMemcpyAsync(h->call_dev, h->call_pin, kCallBlockBytes, cudaMemcpyHostToDevice, h->stream));
     return B2S_OK;
 }
 
@@ -696,8 +721,8 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         if (cfg->coarse_solver == B2S_COARSE_CG)
             MG_CUDA(cudaMalloc(&h->cg_work, 4 * (size_t)h->nx[L - 1] * h->ny[L - 1] * sizeof(double)));
     }
-    MG_CUDA(cudaMalloc(&h->call_dev, sizeof(MGCall)));
-    MG_CUDA(cudaMallocHost(&h->call_pin, 2 * sizeof(MGCall)));
+    MG_CUDA(cudaMalloc(&h->call_dev, kCallBlockBytes));
+    MG_CUDA(cudaMallocHost(&h->call_pin, kCallBlockBytes + sizeof(MGCall)));
     MG_CUDA(cudaMalloc(&h->hist_dev, kMaxHist * sizeof(double)));
     MG_CUDA(cudaMallocHost(&h->hist_pin, kMaxHist * sizeof(double)));
     MG_CUDA(cudaMalloc(&h->sumsq_dev, 8 * sizeof(double)));
@@ -762,7 +787,7 @@ int b2s_mg_solve(b2s_mg *h, double *u, const double *f, double hgrid, double c, 
     // The loop "for iter = 1:niters ... break if r_rms < tolf" (multigrid.jl:58-76) runs on the device: the last kernel
     // of every cycle evaluates the test and raises a flag that turns all later cycles into no-ops. The host enqueues
     // cycles in batches sized from the observed contraction factor and polls one struct per batch.
-    MGCall *back = h->call_pin + 1;
+    MGCall *back = call_back(h);
     back->done = niters > 0 ? 0 : 1;
     back->ncycles = 0;
     int launched = 0;

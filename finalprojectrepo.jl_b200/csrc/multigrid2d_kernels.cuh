@@ -18,6 +18,19 @@ namespace b2s {
 
 constexpr int kMaxLevels = 24;
 
+// Per-level constants of a call, computed once on the host (plain IEEE arithmetic, no contraction: the same values the
+// kernels used to derive per thread with two FP64 divisions) and uploaded together with the call arguments.
+struct LevelCoef {
+    double h;        // h * 2^level, doubled level by level (multigrid.jl:133)
+    double C;        // 4 + c h^2
+    double _h2;      // 1 / h^2
+    double wJ;       // damped-Jacobi weight (4/5) (h^2 / C)   multigrid.jl:245-258
+    double h2;       // h^2
+    double wGS;      // Gauss-Seidel weight 1.0 (h^2 / C)      multigrid.jl:286
+    double inv_h2;   // exact reciprocal of h^2 when it is a power of two (DivH2), else 0
+    int exact, pad;
+};
+
 // Per-call arguments live in device memory so that a captured CUDA graph of the V-cycle is independent of them.
 struct MGCall {
     double *u;          // finest-level unknown (caller's array)
@@ -36,6 +49,7 @@ struct MGCall {
     double *hist;       // r_rms / f_rms per cycle (capacity kMaxHist)
     int rb_combine;     // 1: sumsq[0] = sumsq[2] + sumsq[3] (red + black) before the test
     int pad;
+    const LevelCoef *lev;  // [kMaxLevels], device memory right behind this struct
 };
 constexpr int kMaxHist = 4096;
 
@@ -76,6 +90,14 @@ __device__ __forceinline__ Coef make_coef(double h, double c, double alpha)
 // The Gauss-Seidel residual is written with "/ h^2" in the reference (multigrid.jl:279-283). When h^2 is a power of two
 // (every grid with h = 1/2^k: all the configured shapes) x / h^2 and x * (1/h^2) are the same correctly rounded value, so
 // the ~20-instruction FP64 division is replaced by one multiplication without changing a bit; any other h divides.
+__device__ __forceinline__ Coef level_coef(const MGCall *cp, int level)
+{
+    const LevelCoef *L = cp->lev + level;
+    Coef k;
+    k.C = L->C; k._h2 = L->_h2; k.w = L->wJ;
+    return k;
+}
+
 struct DivH2 {
     double h2, inv;
     bool exact;
@@ -370,7 +392,7 @@ __global__ void __launch_bounds__(kMGBX) mg_prolong_smooth_kernel(const ProlongS
     if (cp->done) return;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int i = blockIdx.x * kMGBX + threadIdx.x;
     if (i >= nx) return;
@@ -477,18 +499,26 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int gx0 = X0 - 3, gy0 = Y0 - 3;
-    // stage u on tile+3 and rhs on tile+2 (asynchronous copies: all loads of the block are in flight at once)
-    for (int idx = threadIdx.x; idx < (kTW + 6) * kTRows; idx += kTileThreads) {
-        const int r = idx / (kTW + 6), c = idx - r * (kTW + 6);
-        const int i = gx0 + c, j = gy0 + r;
-        const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
-        const size_t p = in ? (size_t)i + (size_t)nx * j : 0;
-        cp_async8(A + r * kTP + c, u + p, in);
-        cp_async8(F + r * kTP + c, rhs + p, in && c >= 1 && c < kTW + 5 && r >= 1 && r < kTRows - 1);
+    // stage u on tile+3 and rhs on tile+2 (asynchronous copies: all loads of the block are in flight at once).
+    // One warp per staged row, lanes along x: no per-element division, the row pointer and the row tests are hoisted.
+    for (int r = threadIdx.x >> 5; r < kTRows; r += kTileThreads / 32) {
+        const int j = gy0 + r;
+        const bool jin = j >= 0 && j < ny;
+        const size_t rowoff = jin ? (size_t)nx * j : 0;
+        const bool frow = jin && r >= 1 && r < kTRows - 1;
+        double *Ar = A + r * kTP, *Fr = F + r * kTP;
+#pragma unroll
+        for (int c = threadIdx.x & 31; c < kTW + 6; c += 32) {
+            const int i = gx0 + c;
+            const bool in = jin && i >= 0 && i < nx;
+            const size_t p = in ? rowoff + i : 0;
+            cp_async8(Ar + c, u + p, in);
+            cp_async8(Fr + c, rhs + p, in && frow && c >= 1 && c < kTW + 5);
+        }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -566,26 +596,37 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int gx0 = X0 - 3, gy0 = Y0 - 3;
     const int cx0 = X0 / 2 - 1, cy0 = Y0 / 2 - 1;
-    // stage the smoothed u on tile+2, rhs on tile+1 and the coarse correction window
-    for (int idx = threadIdx.x; idx < (kTW + 4) * (kTH + 4); idx += kTileThreads) {
-        const int r = idx / (kTW + 4), c = idx - r * (kTW + 4);
-        const int i = X0 - 2 + c, j = Y0 - 2 + r;
-        const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
-        const size_t p = in ? (size_t)i + (size_t)nx * j : 0;
-        const int s = (r + 1) * kTP + c + 1;
-        cp_async8(A + s, a.u_in + p, in);
-        cp_async8(F + s, rhs + p, in && c >= 1 && c < kTW + 3 && r >= 1 && r < kTH + 3);
+    // stage the smoothed u on tile+2, rhs on tile+1 and the coarse correction window (one warp per row, lanes along x)
+    for (int r = threadIdx.x >> 5; r < kTH + 4; r += kTileThreads / 32) {
+        const int j = Y0 - 2 + r;
+        const bool jin = j >= 0 && j < ny;
+        const size_t rowoff = jin ? (size_t)nx * j : 0;
+        const bool frow = jin && r >= 1 && r < kTH + 3;
+        double *Ar = A + (r + 1) * kTP + 1, *Fr = F + (r + 1) * kTP + 1;
+#pragma unroll
+        for (int c = threadIdx.x & 31; c < kTW + 4; c += 32) {
+            const int i = X0 - 2 + c;
+            const bool in = jin && i >= 0 && i < nx;
+            const size_t p = in ? rowoff + i : 0;
+            cp_async8(Ar + c, a.u_in + p, in);
+            cp_async8(Fr + c, rhs + p, in && frow && c >= 1 && c < kTW + 3);
+        }
     }
-    for (int idx = threadIdx.x; idx < kCW * kCH; idx += kTileThreads) {
-        const int r = idx / kCW, c = idx - r * kCW;
-        const int I = cx0 + c, J = cy0 + r;
-        const bool in = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;  // the boundary ring counts as 0
-        cp_async8(Cw + idx, a.ec + (in ? (size_t)I + (size_t)nxc * J : 0), in);
+    for (int r = threadIdx.x >> 5; r < kCH; r += kTileThreads / 32) {
+        const int J = cy0 + r;
+        const bool jin = J >= 1 && J <= nyc - 2;  // the boundary ring counts as 0
+        const size_t rowoff = jin ? (size_t)nxc * J : 0;
+#pragma unroll
+        for (int c = threadIdx.x & 31; c < kCW; c += 32) {
+            const int I = cx0 + c;
+            const bool in = jin && I >= 1 && I <= nxc - 2;
+            cp_async8(Cw + r * kCW + c, a.ec + (in ? rowoff + I : 0), in);
+        }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -702,7 +743,7 @@ __global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_down_stream_ker
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int t = threadIdx.x, c = t + 1;
     const int X0 = blockIdx.x * kSW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);
@@ -803,7 +844,7 @@ __global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_up_stream_kerne
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int t = threadIdx.x, c = t + 1;
     const int X0 = blockIdx.x * kSW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);  // ch is even
@@ -983,7 +1024,7 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_down_stream2_kernel(const TileA
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int t = threadIdx.x, ci = 2 * t + 2;  // index of the thread's first column in a ring row (before the shift)
     const int X0 = blockIdx.x * kS2W, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);
@@ -1107,7 +1148,7 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int t = threadIdx.x, ci = 2 * t + 2;
     const int X0 = blockIdx.x * kS2W, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);  // ch even
@@ -1294,7 +1335,7 @@ __global__ void __launch_bounds__(32) mg_down_warp_kernel(const TileArgs a, int 
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int lane = threadIdx.x, ci = 2 * lane + 2;
     const int X0 = blockIdx.x * kWW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);
@@ -1384,7 +1425,7 @@ __global__ void __launch_bounds__(32) mg_up_warp_kernel(const TileArgs a, int ch
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
     const int apply_bcs = cp->apply_bcs;
-    const Coef k = make_coef(level_h(cp, a.level), cp->c, 4.0 / 5.0);
+    const Coef k = level_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int lane = threadIdx.x, ci = 2 * lane + 2;
     const int X0 = blockIdx.x * kWW, Y0 = blockIdx.y * ch, Y1 = min(Y0 + ch, ny);  // ch even

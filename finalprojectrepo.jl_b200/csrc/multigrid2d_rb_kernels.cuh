@@ -49,6 +49,14 @@ __device__ __forceinline__ RbCoef make_rb_coef(double h, double c)
     return k;
 }
 
+__device__ __forceinline__ RbCoef level_rb_coef(const MGCall *cp, int level)
+{
+    const LevelCoef *L = cp->lev + level;
+    RbCoef k;
+    k.C = L->C; k.h2 = L->h2; k.w = L->wGS; k.inv_h2 = L->inv_h2;
+    return k;
+}
+
 // Stage a window of a natural-layout global array into the two colour planes (asynchronous 8-byte copies; elements
 // outside the domain are zero-filled). (gx0, gy0) = global coordinates of window element (0,0); gx0 + gy0 is even, so
 // the local parity (c + r) & 1 is the global colour. Elements outside [c0, c1) x [r0, r1) are skipped.
@@ -56,13 +64,17 @@ template <int kW, int kRows, int kP2>
 __device__ __forceinline__ void rb_stage(double *__restrict__ red, double *__restrict__ blk, const double *__restrict__ g, int gx0,
                                          int gy0, int nx, int ny, int c0, int c1, int r0, int r1)
 {
-    for (int idx = threadIdx.x; idx < kW * kRows; idx += kTileThreads) {
-        const int r = idx / kW, c = idx - r * kW;
-        if (c < c0 || c >= c1 || r < r0 || r >= r1) continue;
-        const int i = gx0 + c, j = gy0 + r;
-        const bool in = i >= 0 && j >= 0 && i < nx && j < ny;
-        double *dst = (((c + r) & 1) ? blk : red) + r * kP2 + (c >> 1);
-        cp_async8(dst, g + (in ? (size_t)i + (size_t)nx * j : 0), in);
+    for (int r = r0 + (threadIdx.x >> 5); r < r1; r += kTileThreads / 32) {  // one warp per staged row, lanes along x
+        const int j = gy0 + r;
+        const bool jin = j >= 0 && j < ny;
+        const size_t rowoff = jin ? (size_t)nx * j : 0;
+        double *rowR = red + r * kP2, *rowB = blk + r * kP2;
+#pragma unroll
+        for (int c = c0 + (threadIdx.x & 31); c < c1; c += 32) {
+            const int i = gx0 + c;
+            const bool in = jin && i >= 0 && i < nx;
+            cp_async8((((c + r) & 1) ? rowB : rowR) + (c >> 1), g + (in ? rowoff + i : 0), in);
+        }
     }
 }
 
@@ -144,9 +156,8 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_rb_kernel(const TileArgs
     const double *u = a.u_in, *rhs = a.rhs;
     if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
     const int apply_bcs = cp->apply_bcs;
-    const double hl = level_h(cp, a.level);
-    const RbCoef k = make_rb_coef(hl, cp->c);
-    const Coef kr = make_coef(hl, cp->c, 1.0);
+    const RbCoef k = level_rb_coef(cp, a.level);
+    const Coef kr = level_coef(cp, a.level);  // C and 1/h^2 of the residual (the weight is not used)
     const int nx = a.nx, ny = a.ny;
     const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
     const int gx0 = X0 - HALO, gy0 = Y0 - HALO;
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_rb_kernel(const TileArgs
     __syncthreads();
     // block-uniform: does the widest window (halo 5) stay strictly inside the domain?
     const bool inner = X0 - 5 >= 1 && Y0 - 5 >= 1 && X0 + TW + 4 <= nx - 2 && Y0 + TH + 4 <= ny - 2;
-    const bool div = !make_div_h2(k.h2).exact;
+    const bool div = !cp->lev[a.level].exact;
     if (inner && !div) rb_down_sweeps<TW, TH, false, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else if (inner) rb_down_sweeps<TW, TH, false, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else if (!div) rb_down_sweeps<TW, TH, true, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
     double *out = a.u_out;
     if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
     const int apply_bcs = cp->apply_bcs;
-    const RbCoef k = make_rb_coef(level_h(cp, a.level), cp->c);
+    const RbCoef k = level_rb_coef(cp, a.level);
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
     const int gx0 = X0 - HALO, gy0 = Y0 - HALO;
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
     }
     __syncthreads();
     const bool inner = X0 - 3 >= 1 && Y0 - 3 >= 1 && X0 + TW + 2 <= nx - 2 && Y0 + TH + 2 <= ny - 2;
-    const bool div = !make_div_h2(k.h2).exact;
+    const bool div = !cp->lev[a.level].exact;
     double acc;
     if (inner && !div) acc = rb_up_sweeps<TW, TH, false, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else if (inner) acc = rb_up_sweeps<TW, TH, false, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
