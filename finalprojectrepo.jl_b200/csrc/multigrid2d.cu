@@ -56,10 +56,10 @@ struct b2s_mg {
     double *partials = nullptr;
     unsigned int *ticket = nullptr;
     cudaStream_t stream = nullptr;
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [bc_before]
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long kernel_launches = 0;
-    long long launches_per_cycle = 0;
+    long long launches_per_cycle[2] = {0, 0};
     double last_ms = 0.0;
     int tile_choice = -1;
     int tile_min_blocks = 400;
@@ -185,14 +185,14 @@ int cg_global(double *x_in, const double *b, double *work, double hx, double hy,
               cudaStream_t st, double *ss_out, int *iters_out, long long *count);
 
 // Enqueues one V-cycle (multigrid.jl:91-170) on `st`; counts kernel launches.
-int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
+int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
 {
     const b2s_mg_config &c = h->cfg;
     const MGCall *cp = h->call_dev;
     long long n = 0;
     const bool rb = c.smoother == B2S_SMOOTH_RBGS;
-    // apply_boundary_conditions!(u) before the cycle (no-op unless cp->bc_before)
-    {
+    // apply_boundary_conditions!(u) before the cycle (multigrid.jl:60-62); calls without it use a graph without the node
+    if (with_bc) {
         const int t = h->nx[0] + h->ny[0];
         mg_bc_kernel<<<(t + 255) / 256, 256, 0, st>>>(cp, nullptr, h->nx[0], h->ny[0], 0);
         ++n;
@@ -229,6 +229,8 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     const int fs = h->coarse_global ? h->nlev - 1 : h->first_smem;
     const bool fused_b = fused_variant_b(c);
     const bool fused = fused_variant_a(c) || fused_b;
+    // the finest level's fused upward kernel finishes the cycle itself (norm -> r_rms -> exit test) when there is one
+    const bool end_fused = fused && (h->coarse_global ? h->nlev - 1 : h->first_smem) > 0;
     auto tile_args = [&](int l) {
         TileArgs t = {};
         t.cp = cp; t.level = l; t.rhs = h->rhs[l]; t.nx = h->nx[l]; t.ny = h->ny[l]; t.nxc = h->nx[l + 1]; t.nyc = h->ny[l + 1];
@@ -363,6 +365,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
     for (int l = fs - 1; l >= 0 && fused; --l) {
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
+        t.fused_end = (l == 0 && end_fused) ? 1 : 0;
         if (fused_b) {
             launch_rb_tile(rb_choice(l), true, t, st);
         } else if (use_streaming(l) && warp_kind) {
@@ -405,8 +408,10 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count)
             ++n;
         }
     }
-    mg_cycle_end_kernel<<<1, 32, 0, st>>>(h->call_dev);  // r_rms, exit test, bookkeeping (multigrid.jl:64-75)
-    ++n;
+    if (!end_fused) {
+        mg_cycle_end_kernel<<<1, 32, 0, st>>>(h->call_dev);  // r_rms, exit test, bookkeeping (multigrid.jl:64-75)
+        ++n;
+    }
     B2S_CUDA(cudaGetLastError());
     if (count) *count = n;
     return B2S_OK;
@@ -514,24 +519,25 @@ int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count)
 
 int launch_cycle(b2s_mg *h)
 {
+    const int bc = h->call_pin->bc_before ? 1 : 0;  // two graphs: with / without the boundary-condition node
     if (h->cfg.use_graph) {
-        if (!h->graph) {
+        if (!h->graph[bc]) {
             cudaGraph_t g = nullptr;
             B2S_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             long long n = 0;
-            int rc = enqueue_vcycle(h, h->stream, &n);
+            int rc = enqueue_vcycle(h, h->stream, &n, bc != 0);
             cudaError_t e = cudaStreamEndCapture(h->stream, &g);
             if (rc != B2S_OK) { if (g) cudaGraphDestroy(g); return rc; }
             B2S_CUDA(e);
-            h->launches_per_cycle = n;
-            B2S_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+            h->launches_per_cycle[bc] = n;
+            B2S_CUDA(cudaGraphInstantiate(&h->graph[bc], g, 0));
             B2S_CUDA(cudaGraphDestroy(g));
         }
-        B2S_CUDA(cudaGraphLaunch(h->graph, h->stream));
-        h->kernel_launches += h->launches_per_cycle;
+        B2S_CUDA(cudaGraphLaunch(h->graph[bc], h->stream));
+        h->kernel_launches += h->launches_per_cycle[bc];
     } else {
         long long n = 0;
-        B2S_CHECK(enqueue_vcycle(h, h->stream, &n));
+        B2S_CHECK(enqueue_vcycle(h, h->stream, &n, bc != 0));
         h->kernel_launches += n;
     }
     return B2S_OK;
@@ -582,7 +588,8 @@ int mg_destroy_impl(b2s_mg *h)
     if (!h) return B2S_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->graph) cudaGraphExecDestroy(h->graph);
+    for (int g_ = 0; g_ < 2; ++g_)
+        if (h->graph[g_]) cudaGraphExecDestroy(h->graph[g_]);
     for (int l = 0; l < kMaxLevels; ++l) {
         if (h->u[l]) cudaFree(h->u[l]);
         if (h->rhs[l]) cudaFree(h->rhs[l]);
@@ -855,7 +862,7 @@ int b2s_mg_cycles(b2s_mg *h, double *u, const double *f, double hgrid, double c,
     DeviceGuard guard;
     guard.set(h->cfg.device);
     B2S_CHECK(set_call(h, u, f, hgrid, c, tol, apply_bcs, apply_bcs, 1 << 30, 0));
-    if (h->cfg.use_graph && !h->graph && ncycles > 0) {  // keep graph instantiation out of the timed region
+    if (h->cfg.use_graph && !h->graph[apply_bcs ? 1 : 0] && ncycles > 0) {  // keep graph instantiation out of the timed region
         B2S_CHECK(launch_cycle(h));
         B2S_CUDA(cudaStreamSynchronize(h->stream));
         --ncycles;

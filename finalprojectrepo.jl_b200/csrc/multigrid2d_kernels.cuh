@@ -53,10 +53,16 @@ struct MGCall {
 };
 constexpr int kMaxHist = 4096;
 
-// End of a V-cycle: r_rms, convergence test and bookkeeping on the device (multigrid.jl:64-75).
+// End of a V-cycle: r_rms, convergence test and bookkeeping on the device (multigrid.jl:64-75). One thread. The fused
+// upward kernels of the finest level run it in the block that completes the residual norm (no separate launch).
+__device__ __forceinline__ void cycle_end(MGCall *cp);
 __global__ void mg_cycle_end_kernel(MGCall *cp)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0 || cp->done) return;
+    cycle_end(cp);
+}
+__device__ __forceinline__ void cycle_end(MGCall *cp)
+{
     double *ss = cp->sumsq;
     if (cp->rb_combine) ss[0] = ss[2] + ss[3];
     const double r_rms = sqrt(ss[0] / cp->n_points);
@@ -446,6 +452,7 @@ struct TileArgs {
     double *partials;
     unsigned int *ticket;
     double *sumsq_out;
+    int fused_end;        // up, finest level: the block that completes the norm also runs cycle_end()
 };
 
 // 8-byte asynchronous global->shared copy (LDGSTS); pred == false zero-fills the destination without reading.
@@ -662,7 +669,10 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
         const double bsum = block_sum(acc, red);
         double total;
-        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) {
+            *a.sumsq_out = total;
+            if (a.fused_end) cycle_end(const_cast<MGCall *>(a.cp));
+        }
     }
 }
 
@@ -950,7 +960,10 @@ __global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_up_stream_kerne
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
         const double bsum = block_sum(acc, red);
         double total;
-        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) {
+            *a.sumsq_out = total;
+            if (a.fused_end) cycle_end(const_cast<MGCall *>(a.cp));
+        }
     }
 }
 
@@ -1280,7 +1293,10 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
         const double bsum = block_sum(acc, red);
         double total;
-        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) {
+            *a.sumsq_out = total;
+            if (a.fused_end) cycle_end(const_cast<MGCall *>(a.cp));
+        }
     }
 }
 
@@ -1525,7 +1541,10 @@ __global__ void __launch_bounds__(32) mg_up_warp_kernel(const TileArgs a, int ch
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
         const double bsum = block_sum(acc, red);
         double total;
-        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) {
+            *a.sumsq_out = total;
+            if (a.fused_end) cycle_end(const_cast<MGCall *>(a.cp));
+        }
     }
 }
 

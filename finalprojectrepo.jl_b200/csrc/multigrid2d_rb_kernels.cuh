@@ -284,7 +284,10 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
         const double bsum = block_sum(acc, red);
         double total;
-        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) *a.sumsq_out = total;
+        if (grid_sum_last_block(bsum, a.partials, a.ticket, nblocks, bl, red, &total)) {
+            *a.sumsq_out = total;
+            if (a.fused_end) cycle_end(const_cast<MGCall *>(a.cp));
+        }
     }
 }
 
