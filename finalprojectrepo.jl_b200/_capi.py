@@ -35,7 +35,8 @@ class B2SError(RuntimeError):
 class Diff3DConfig(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nslabs_total", C.c_int), ("slab_begin", C.c_int),
                 ("slab_count", C.c_int), ("devices", _ip), ("halo_mode", C.c_int), ("bc_mode", C.c_int),
-                ("scale_physical_size", C.c_int), ("kernel_variant", C.c_int), ("batch", C.c_int)]
+                ("scale_physical_size", C.c_int), ("kernel_variant", C.c_int), ("batch", C.c_int),
+                ("dimx", C.c_int), ("dimy", C.c_int)]
 
 
 class Diff3DParams(C.Structure):

@@ -212,6 +212,7 @@ struct DeviceCtx {  // one per distinct device of the handle: stream, PT state, 
     double *err_hist = nullptr;
     int err_hist_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_bar = nullptr;  // cross-device ordering of the plane copies (general decompositions)
 };
 
 }  // namespace
@@ -230,6 +231,7 @@ struct b2s_diff3d {
     int nblocks = 0;
     int nslots_dst = 0;           // RankSlots instances that receive partials (devices in-process, ranks multi-process)
     bool multi = false;           // more than one slab in the global stack
+    bool cart = false;            // decomposition in x or y as well: update_halo! as separate plane copies
     bool connected = false;       // multi-process: peers mapped
     std::vector<void *> ipc_mapped;
     long long launched = 0;       // PT iterations since create (host mirror of PTState::total_iters)
@@ -254,6 +256,81 @@ int slab_index(const b2s_diff3d *h, int global_slab)
 {
     const int i = global_slab - h->cfg.slab_begin;
     return (i >= 0 && i < (int)h->slabs.size()) ? i : -1;
+}
+
+// dims of the rank grid and the coordinates of a rank (MPI Cartesian order: z fastest)
+void cart_dims(const b2s_diff3d_config &c, int dims[3])
+{
+    dims[0] = c.dimx > 1 ? c.dimx : 1;
+    dims[1] = c.dimy > 1 ? c.dimy : 1;
+    dims[2] = c.nslabs_total / (dims[0] * dims[1]);
+}
+void cart_coords(const b2s_diff3d_config &c, int rank, int coord[3])
+{
+    int dims[3];
+    cart_dims(c, dims);
+    coord[2] = rank % dims[2];
+    coord[1] = (rank / dims[2]) % dims[1];
+    coord[0] = rank / (dims[2] * dims[1]);
+}
+bool is_cart(const b2s_diff3d_config &c) { return (c.dimx > 1 ? c.dimx : 1) * (c.dimy > 1 ? c.dimy : 1) > 1; }
+
+// every device stream waits for the work enqueued so far on all the others (no-op with one device)
+int cross_device_barrier(b2s_diff3d *h)
+{
+    if (h->devs.size() < 2) return B2S_OK;
+    for (DeviceCtx &d : h->devs) {
+        B2S_CUDA(cudaSetDevice(d.dev));
+        B2S_CUDA(cudaEventRecord(d.ev_bar, d.stream));
+    }
+    for (DeviceCtx &d : h->devs) {
+        B2S_CUDA(cudaSetDevice(d.dev));
+        for (DeviceCtx &o : h->devs)
+            if (&o != &d) B2S_CUDA(cudaStreamWaitEvent(d.stream, o.ev_bar, 0));
+    }
+    return B2S_OK;
+}
+
+// update_halo!(buf[which]) of ImplicitGlobalGrid for a general decomposition: per axis x, y, z the low rank's plane n-2
+// goes to the high rank's plane 0 and the high rank's plane 1 to the low rank's plane n-1 (whole planes, overlap 2).
+// The reference exchanges the buffer the step kernel has just READ (part1_kernel_programming.jl:182,187: halos lag two
+// iterations) -- `which` selects it; the consistent mode passes the buffer just written.
+int cart_update_halo(b2s_diff3d *h, int which)
+{
+    const b2s_diff3d_config &c = h->cfg;
+    int dims[3];
+    cart_dims(c, dims);
+    const int nd[3] = {c.nx, c.ny, c.nz};
+    B2S_CHECK(cross_device_barrier(h));  // all step kernels done before anyone's halo cells change
+    for (int axis = 0; axis < 3; ++axis) {
+        if (dims[axis] == 1) continue;
+        const size_t plane = (size_t)nd[(axis + 1) % 3] * nd[(axis + 2) % 3];
+        const int blocks = (int)std::min<size_t>((plane + 255) / 256, 592);
+        for (size_t i = 0; i < h->slabs.size(); ++i) {
+            Slab &lo = h->slabs[i];
+            int coord[3];
+            cart_coords(c, lo.rank, coord);
+            if (coord[axis] + 1 >= dims[axis]) continue;
+            int ch[3] = {coord[0], coord[1], coord[2]};
+            ch[axis] += 1;
+            Slab &hi = h->slabs[(size_t)((ch[0] * dims[1] + ch[1]) * dims[2] + ch[2])];
+            const int n = nd[axis];
+            {  // low rank's plane n-2 -> high rank's plane 0 (on the receiver's stream)
+                DeviceCtx &d = h->devs[hi.devslot];
+                B2S_CUDA(cudaSetDevice(hi.dev));
+                halo_plane_copy_kernel<<<blocks, 256, 0, d.stream>>>(lo.buf[which], hi.buf[which], axis, n - 2, 0, c.nx, c.ny, c.nz, d.state);
+            }
+            {  // high rank's plane 1 -> low rank's plane n-1
+                DeviceCtx &d = h->devs[lo.devslot];
+                B2S_CUDA(cudaSetDevice(lo.dev));
+                halo_plane_copy_kernel<<<blocks, 256, 0, d.stream>>>(hi.buf[which], lo.buf[which], axis, 1, n - 1, c.nx, c.ny, c.nz, d.state);
+            }
+            h->kernel_launches += 2;
+        }
+        B2S_CUDA(cudaGetLastError());
+        B2S_CHECK(cross_device_barrier(h));  // the next axis forwards cells this one has just written
+    }
+    return B2S_OK;
 }
 
 int launch_iteration(b2s_diff3d *h)
@@ -287,6 +364,7 @@ int launch_iteration(b2s_diff3d *h)
         else B2S_CHECK(launch_direct(p, d.stream));
         h->kernel_launches += 1;
     }
+    if (h->cart) B2S_CHECK(cart_update_halo(h, h->cfg.halo_mode == B2S_HALO_CONSISTENT ? (par ^ 1) : par));
     if (h->multi) {
         for (DeviceCtx &d : h->devs) {
             B2S_CUDA(cudaSetDevice(d.dev));
@@ -376,11 +454,13 @@ int ensure_hist(b2s_diff3d *h, int n)
 
 void compute_params_raw(const b2s_diff3d_config &c, b2s_diff3d_params &p)
 {
-    // part1_kernel_programming.jl:104-131 with dims = (1,1,nslabs_total)
+    // part1_kernel_programming.jl:104-131 with dims = (dimx, dimy, nslabs_total / (dimx*dimy))
     const double D = 1.0;
+    int dims[3];
+    cart_dims(c, dims);
     p.lx = 10.0; p.ly = 10.0; p.lz = 10.0;
-    if (c.scale_physical_size) { p.lx = 1 * 10.0; p.ly = 1 * 10.0; p.lz = c.nslabs_total * 10.0; }
-    p.nx_g = 1 * (c.nx - 2) + 2; p.ny_g = 1 * (c.ny - 2) + 2; p.nz_g = c.nslabs_total * (c.nz - 2) + 2;
+    if (c.scale_physical_size) { p.lx = dims[0] * 10.0; p.ly = dims[1] * 10.0; p.lz = dims[2] * 10.0; }
+    p.nx_g = dims[0] * (c.nx - 2) + 2; p.ny_g = dims[1] * (c.ny - 2) + 2; p.nz_g = dims[2] * (c.nz - 2) + 2;
     p.dx = p.lx / p.nx_g; p.dy = p.ly / p.ny_g; p.dz = p.lz / p.nz_g;
     p.total_N = (double)c.nslabs_total * c.nx * c.ny * c.nz;
     p.dt = 0.2;
@@ -407,6 +487,7 @@ int destroy_impl(b2s_diff3d *h)
         if (d.err_hist) cudaFree(d.err_hist);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev_bar) cudaEventDestroy(d.ev_bar);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     for (Slab &s : h->slabs) {
@@ -437,6 +518,13 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
     B2S_REQUIRE(cfg->halo_mode == B2S_HALO_REFERENCE_LAG2 || cfg->halo_mode == B2S_HALO_CONSISTENT, B2S_ERR_BAD_ARG,
                 "bad halo_mode");
     B2S_REQUIRE(cfg->bc_mode == B2S_BC_LITERAL || cfg->bc_mode == B2S_BC_PROPER, B2S_ERR_BAD_ARG, "bad bc_mode");
+    {
+        const int dx_ = cfg->dimx > 1 ? cfg->dimx : 1, dy_ = cfg->dimy > 1 ? cfg->dimy : 1;
+        B2S_REQUIRE(cfg->dimx >= 0 && cfg->dimy >= 0 && cfg->nslabs_total % (dx_ * dy_) == 0, B2S_ERR_BAD_ARG,
+                    "dims (%d, %d, .) do not divide %d ranks", cfg->dimx, cfg->dimy, cfg->nslabs_total);
+        B2S_REQUIRE(dx_ * dy_ == 1 || cfg->slab_count == cfg->nslabs_total, B2S_ERR_NOT_IMPLEMENTED,
+                    "a decomposition in x or y needs an in-process handle (slab_count == nslabs_total)");
+    }
     int ndev = 0;
     B2S_CHECK(b2s_device_count(&ndev));
     B2S_REQUIRE(ndev > 0, B2S_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
@@ -459,6 +547,7 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
     }
     compute_params(h);
     h->multi = cfg->nslabs_total > 1;
+    h->cart = is_cart(*cfg);
     h->ar.layout((size_t)cfg->nx * cfg->ny * cfg->nz);
 
 #define FAIL_IF(call)                      \
@@ -562,10 +651,17 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
                 if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
                 else CUDA_FAIL_IF(e);
             }
-        for (size_t i = 0; i < h->slabs.size(); ++i) {
-            Slab &s = h->slabs[i];
-            if (i > 0) { s.lo_buf[0] = h->slabs[i - 1].buf[0]; s.lo_buf[1] = h->slabs[i - 1].buf[1]; }
-            if (i + 1 < h->slabs.size()) { s.hi_buf[0] = h->slabs[i + 1].buf[0]; s.hi_buf[1] = h->slabs[i + 1].buf[1]; }
+        if (!h->cart) {  // z-slabs: the halo push is fused into the step kernel
+            for (size_t i = 0; i < h->slabs.size(); ++i) {
+                Slab &s = h->slabs[i];
+                if (i > 0) { s.lo_buf[0] = h->slabs[i - 1].buf[0]; s.lo_buf[1] = h->slabs[i - 1].buf[1]; }
+                if (i + 1 < h->slabs.size()) { s.hi_buf[0] = h->slabs[i + 1].buf[0]; s.hi_buf[1] = h->slabs[i + 1].buf[1]; }
+            }
+        } else {
+            for (DeviceCtx &d : h->devs) {
+                CUDA_FAIL_IF(cudaSetDevice(d.dev));
+                CUDA_FAIL_IF(cudaEventCreateWithFlags(&d.ev_bar, cudaEventDisableTiming));
+            }
         }
         std::vector<RankSlots *> tbl;
         for (DeviceCtx &d : h->devs) tbl.push_back(d.slots);
@@ -641,8 +737,9 @@ int b2s_diff3d_init_gaussian(b2s_diff3d *h)
     const double cx = p.lx / 2, cy = p.ly / 2, cz = p.lz / 2;
     for (size_t si = 0; si < h->slabs.size(); ++si) {
         double *Ht = host.data() + si * n;
-        const int coord[3] = {0, 0, h->slabs[si].rank};
-        const int dims[3] = {1, 1, c.nslabs_total};
+        int coord[3], dims[3];
+        cart_coords(c, h->slabs[si].rank, coord);
+        cart_dims(c, dims);
 #pragma omp parallel for schedule(static)
         for (int k = 0; k < nz; ++k)
             for (int j = 0; j < ny; ++j)
@@ -849,8 +946,25 @@ int b2s_diff3d_gather(b2s_diff3d *h, double *H_g_host)
 {
     B2S_REQUIRE(h && H_g_host, B2S_ERR_BAD_ARG, "NULL argument");
     // H_g has size (nx*dims[1], ny*dims[2], nz*dims[3]) and receives every rank's whole local Ht (:144,223)
-    for (size_t i = 0; i < h->slabs.size(); ++i)
-        B2S_CHECK(b2s_diff3d_get_field(h, h->slabs[i].rank, 0, H_g_host + i * h->ar.cells));
+    if (!h->cart) {  // z-slabs: rank-major blocks are the global layout
+        for (size_t i = 0; i < h->slabs.size(); ++i)
+            B2S_CHECK(b2s_diff3d_get_field(h, h->slabs[i].rank, 0, H_g_host + i * h->ar.cells));
+        return B2S_OK;
+    }
+    const b2s_diff3d_config &c = h->cfg;
+    int dims[3];
+    cart_dims(c, dims);
+    std::vector<double> loc(h->ar.cells);
+    const size_t gx = (size_t)c.nx * dims[0], gy = (size_t)c.ny * dims[1];
+    for (size_t i = 0; i < h->slabs.size(); ++i) {
+        B2S_CHECK(b2s_diff3d_get_field(h, h->slabs[i].rank, 0, loc.data()));
+        int coord[3];
+        cart_coords(c, h->slabs[i].rank, coord);
+        for (int k = 0; k < c.nz; ++k)
+            for (int j = 0; j < c.ny; ++j)
+                memcpy(H_g_host + ((size_t)coord[0] * c.nx + gx * (((size_t)coord[1] * c.ny + j) + gy * ((size_t)coord[2] * c.nz + k))),
+                       loc.data() + (size_t)c.nx * (j + (size_t)c.ny * k), (size_t)c.nx * sizeof(double));
+    }
     return B2S_OK;
 }
 

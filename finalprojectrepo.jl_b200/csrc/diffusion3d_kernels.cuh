@@ -287,6 +287,26 @@ __global__ void __launch_bounds__((TX / 2) * TY)
     step_epilogue(p, acc, red);
 }
 
+// update_halo! of a general Cartesian decomposition (ImplicitGlobalGrid): one plane of `src` (index sp along `axis`) is
+// copied to plane dp of `dst` -- whole planes including their edges, so values travel across corners through the
+// x -> y -> z sequence exactly as in the reference. src and dst may live on different GPUs (peer access).
+__global__ void __launch_bounds__(256) halo_plane_copy_kernel(const double *__restrict__ src, double *__restrict__ dst, int axis,
+                                                              int sp, int dp, int nx, int ny, int nz, const PTState *state)
+{
+    if (state != nullptr && state->done) return;
+    const int n1 = axis == 0 ? ny : nx;            // fast index of the plane
+    const int n2 = axis == 2 ? ny : nz;            // slow index of the plane
+    const size_t total = (size_t)n1 * n2;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int a = (int)(t % n1), b = (int)(t / n1);
+        size_t ps, pd;
+        if (axis == 0) { ps = (size_t)sp + (size_t)nx * (a + (size_t)ny * b); pd = (size_t)dp + (size_t)nx * (a + (size_t)ny * b); }
+        else if (axis == 1) { ps = (size_t)a + (size_t)nx * (sp + (size_t)ny * b); pd = (size_t)a + (size_t)nx * (dp + (size_t)ny * b); }
+        else { ps = (size_t)a + (size_t)nx * (b + (size_t)ny * sp); pd = (size_t)a + (size_t)nx * (b + (size_t)ny * dp); }
+        dst[pd] = src[ps];
+    }
+}
+
 // One block: consume the partial sums of all ranks in rank order (deterministic, identical on every GPU).
 // In-process handles pass `local` (nranks contiguous doubles on this device); one-process-per-GPU handles pass `slots`
 // and wait (bounded) for the peers' stores.

@@ -28,6 +28,7 @@ struct Diff3DConfig            # b2s_diff3d_config
     nslabs_total::Cint; slab_begin::Cint; slab_count::Cint
     devices::Ptr{Cint}
     halo_mode::Cint; bc_mode::Cint; scale_physical_size::Cint; kernel_variant::Cint; batch::Cint
+    dimx::Cint; dimy::Cint     # general Cartesian decomposition (0/1: z-slabs)
 end
 
 struct Diff3DParams            # b2s_diff3d_params
@@ -47,16 +48,19 @@ end
 
 """
 Drop-in for `diffusion_3D_kernel_programming` (scripts-part1/part1_kernel_programming.jl:99-228).
-`devices` replaces the MPI ranks: one z-slab (dims = (1,1,N)) per listed CUDA device, driven from this process.
+`devices` replaces the MPI ranks: one rank per listed CUDA device (ordinals may repeat), driven from this process.
+By default the ranks are z-slabs (dims = (1,1,N)); `dimx`, `dimy` select ImplicitGlobalGrid's general decomposition
+(dims = (dimx, dimy, N ÷ (dimx*dimy)), ranks in MPI Cartesian order).
 """
 function diffusion_3D_kernel_programming(; nx, ny, nz, ttot=1.0, tol=1e-8, use_shared_memory=true, do_vis=false,
                                          verbose=true, init_and_finalize_MPI=false, scale_physical_size=false,
-                                         devices::Vector{Cint}=Cint[0], halo_mode::Integer=0, bc_mode::Integer=0)
+                                         devices::Vector{Cint}=Cint[0], halo_mode::Integer=0, bc_mode::Integer=0,
+                                         dimx::Integer=1, dimy::Integer=1)
     N = length(devices)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve devices begin
         cfg = Diff3DConfig(nx, ny, nz, N, 0, N, pointer(devices), halo_mode, bc_mode, scale_physical_size ? 1 : 0,
-                           use_shared_memory ? 0 : 1, 0)
+                           use_shared_memory ? 0 : 1, 0, dimx, dimy)
         check(ccall((:b2s_diff3d_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{Diff3DConfig}), h, cfg))
     end
     try

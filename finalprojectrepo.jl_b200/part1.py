@@ -28,9 +28,15 @@ class Diffusion3D:
 
     def __init__(self, nx, ny, nz, nslabs=1, devices=None, slab_begin=0, slab_count=None,
                  halo_mode=capi.HALO_REFERENCE_LAG2, bc_mode=capi.BC_LITERAL, scale_physical_size=False,
-                 kernel_variant=capi.KERNEL_AUTO, batch=0):
+                 kernel_variant=capi.KERNEL_AUTO, batch=0, dims=None):
+        """dims = (dimx, dimy, dimz): general Cartesian rank grid like init_global_grid's (in-process handles only;
+        ranks in MPI Cartesian order, z fastest). Default: z-slabs (1, 1, nslabs)."""
         self._L = capi.lib()
         self.n = (int(nx), int(ny), int(nz))
+        if dims is not None:
+            dims = tuple(int(d) for d in dims)
+            nslabs = dims[0] * dims[1] * dims[2]
+        self.dims = dims if dims is not None else (1, 1, int(nslabs))
         self.nslabs = int(nslabs)
         self.slab_begin = int(slab_begin)
         self.slab_count = self.nslabs if slab_count is None else int(slab_count)
@@ -40,7 +46,7 @@ class Diffusion3D:
         self._devs = (C.c_int * self.slab_count)(*devices)
         cfg = capi.Diff3DConfig(self.n[0], self.n[1], self.n[2], self.nslabs, self.slab_begin, self.slab_count,
                                 C.cast(self._devs, C.POINTER(C.c_int)), halo_mode, bc_mode,
-                                int(bool(scale_physical_size)), kernel_variant, batch)
+                                int(bool(scale_physical_size)), kernel_variant, batch, self.dims[0], self.dims[1])
         self._h = C.c_void_p()
         capi.check(self._L.b2s_diff3d_create(C.byref(self._h), C.byref(cfg)))
         p = capi.Diff3DParams()
@@ -108,8 +114,13 @@ class Diffusion3D:
         return a
 
     def gather(self):
-        """gather!(Array(Ht), H_g): (nx, ny, nz*slab_count), every hosted slab's whole local array."""
-        a = np.zeros((self.n[0], self.n[1], self.n[2] * self.slab_count), dtype=np.float64, order="F")
+        """gather!(Array(Ht), H_g): (nx*dimx, ny*dimy, nz*dimz) -- for z-slabs (nx, ny, nz*slab_count) --, every hosted
+        rank's whole local array at its place in the rank grid."""
+        if self.dims[0] * self.dims[1] > 1:
+            shape = tuple(n * d for n, d in zip(self.n, self.dims))
+        else:
+            shape = (self.n[0], self.n[1], self.n[2] * self.slab_count)
+        a = np.zeros(shape, dtype=np.float64, order="F")
         capi.check(self._L.b2s_diff3d_gather(self._h, capi.ptr(a)))
         return a
 
@@ -136,17 +147,22 @@ class Diffusion3D:
 def diffusion_3D_kernel_programming(*, nx, ny, nz, ttot=1.0, tol=1e-8, use_shared_memory=True, do_vis=False,
                                     verbose=True, init_and_finalize_MPI=True, scale_physical_size=False, nslabs=1,
                                     devices=None, halo_mode=capi.HALO_REFERENCE_LAG2, bc_mode=capi.BC_LITERAL,
-                                    kernel_variant=capi.KERNEL_AUTO, return_iters=False):
+                                    kernel_variant=capi.KERNEL_AUTO, return_iters=False, dims=None):
     """Drop-in for scripts-part1/part1_kernel_programming.jl:99.  Returns (X_g, H_g, BenchResults).
 
     `use_shared_memory` selects the staged (TMA) or the direct kernel; results are bit-identical either way.
-    `nslabs`/`devices` replace the MPI rank count: dims = (1, 1, nslabs) z-slabs, one per device entry.
+    `nslabs`/`devices` replace the MPI rank count: dims = (1, 1, nslabs) z-slabs, one per device entry; `dims` =
+    (dimx, dimy, dimz) selects ImplicitGlobalGrid's general rank grid instead (the published 2x2x1 / 2x2x2 layouts).
     """
+    if dims is not None:
+        nslabs = int(dims[0]) * int(dims[1]) * int(dims[2])
+        if devices is None:
+            devices = [0] * nslabs
     kv = kernel_variant
     if kv == capi.KERNEL_AUTO and not use_shared_memory:
         kv = capi.KERNEL_DIRECT
     s = Diffusion3D(nx, ny, nz, nslabs=nslabs, devices=devices, halo_mode=halo_mode, bc_mode=bc_mode,
-                    scale_physical_size=scale_physical_size, kernel_variant=kv)
+                    scale_physical_size=scale_physical_size, kernel_variant=kv, dims=dims)
     try:
         s.init_gaussian()
         iter_max = 100000  # :130

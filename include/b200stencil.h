@@ -95,6 +95,11 @@ typedef struct {
     int scale_physical_size; /* part1_kernel_programming.jl:110-114 */
     int kernel_variant;      /* B2S_KERNEL_* */
     int batch;               /* PT iterations enqueued per host poll; 0 = automatic */
+    int dimx, dimy;          /* general Cartesian decomposition dims = (dimx, dimy, nslabs_total/(dimx*dimy)) like
+                              * ImplicitGlobalGrid's init_global_grid (part1_kernel_programming.jl:117); 0 or 1 = z-slabs.
+                              * Rank r has coords (r / (dimy*dimz), (r / dimz) % dimy, r % dimz) (MPI Cartesian order).
+                              * dimx*dimy > 1 needs an in-process handle (slab_count == nslabs_total); update_halo! then
+                              * runs as separate plane copies in ImplicitGlobalGrid's order x, y, z after every step. */
 } b2s_diff3d_config;
 
 /* Derived numerics of part1_kernel_programming.jl:117-152. */

@@ -62,6 +62,26 @@ def test_host_geometry_matches_oracle(b2s, oracle, n, nslabs, scale):
     del small
 
 
+@pytest.mark.parametrize("n,dims,scale", [((16, 12, 10), (2, 2, 1), False), ((16, 12, 10), (2, 2, 2), True),
+                                          ((10, 10, 18), (3, 1, 2), True), ((64, 64, 128), (2, 2, 1), False)])
+def test_host_geometry_general_decomposition(b2s, oracle, n, dims, scale):
+    """The same geometry for ImplicitGlobalGrid's general rank grids dims = (dimx, dimy, dimz) (2x2x1, 2x2x2 of the
+    published scaling runs, part1_scaling_experiments.jl): bit-identical to the oracle's rank emulation."""
+    from b200stencil import capi
+    nr = dims[0] * dims[1] * dims[2]
+    cfg = capi.Diff3DConfig(n[0], n[1], n[2], nr, 0, nr, None, 0, 0, int(scale), 0, 0, dims[0], dims[1])
+    p = capi.Diff3DParams()
+    capi.check(capi.lib().b2s_diff3d_params_for(C.byref(cfg), C.byref(p)))
+    if np.prod(n) * nr < 3e6:
+        o = oracle.Diffusion3D(*n, dims=dims, scale_physical_size=scale)
+        assert (p.dx, p.dy, p.dz, p.dt, p.dtau, p.lx, p.ly, p.lz) == (o.dx, o.dy, o.dz, o.dt, o.dtau, o.lx, o.ly, o.lz)
+    assert (p.nx_g, p.ny_g, p.nz_g) == tuple(d * (m - 2) + 2 for d, m in zip(dims, n))
+    assert p.total_N == float(nr) * n[0] * n[1] * n[2]
+    bad = capi.Diff3DConfig(16, 16, 16, 6, 0, 6, None, 0, 0, 0, 0, 0, 4, 1)  # 4 does not divide 6 ranks
+    h = C.c_void_p()
+    assert capi.lib().b2s_diff3d_create(C.byref(h), C.byref(bad)) != 0
+
+
 def test_mg_algorithmic_bytes(b2s):
     from b200stencil import part2
     # SURVEY 8d: 132 B x 1,402,168 points = 185.1 MB per V-cycle at 1025^2
