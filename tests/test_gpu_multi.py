@@ -37,6 +37,28 @@ def test_inprocess_two_devices_match_rank_emulation(b2s, gpu, oracle, halo_mode)
     g.close()
 
 
+@pytest.mark.parametrize("halo_mode", [0, 1])
+@pytest.mark.parametrize("shape,dims", [((64, 32, 18), (2, 2, 1)), ((20, 18, 16), (2, 2, 2))])
+def test_inprocess_general_decomposition_on_two_devices(b2s, gpu, oracle, halo_mode, shape, dims):
+    """A 2x2x1 / 2x2x2 rank grid spread over two GPUs (ranks alternate between the devices): the per-axis plane copies
+    cross the NVLink and are ordered by events between the device streams."""
+    if gpu < 2:
+        pytest.skip("needs 2 GPUs")
+    from b200stencil import part1
+    nr = dims[0] * dims[1] * dims[2]
+    o = oracle.Diffusion3D(*shape, dims=dims, halo_mode=halo_mode)
+    g = part1.Diffusion3D(*shape, dims=dims, devices=[r % 2 for r in range(nr)], halo_mode=halo_mode)
+    g.init_gaussian()
+    for chunk in (1, 2, 3, 30):
+        eo, eg = o.iterate(chunk), g.iterate(chunk)
+        assert np.allclose(eg, eo, rtol=1e-12, atol=0)
+        for r in range(nr):
+            assert np.array_equal(g.get("Htau", r), o.get("Htau", r)), r
+    assert g.solve_timestep(1e-6)[0] == o.solve_timestep(1e-6)[0]
+    assert np.array_equal(g.gather(), o.gather())
+    g.close()
+
+
 @pytest.mark.parametrize("args", [["64", "64", "34", "0", "tma"], ["32", "32", "18", "1", "direct"]])
 def test_one_process_per_gpu_matches_rank_emulation(b2s, gpu, args):
     if gpu < 2:
