@@ -143,10 +143,15 @@ void launch_rb_tile(int choice, bool up, const TileArgs &t, cudaStream_t st)
     case 5: launch_rb_tile_t<32, 16>(up, t, st); break;
     case 6: launch_rb_tile_t<16, 16>(up, t, st); break;
     case 7: launch_rb_tile_t<16, 8>(up, t, st); break;
+    case 8: launch_rb_tile_t<52, 32>(up, t, st); break;   // staged width 64: the half sweeps run row-wise
+    case 9: launch_rb_tile_t<52, 16>(up, t, st); break;
+    case 10: launch_rb_tile_t<20, 16>(up, t, st); break;  // staged width 32
+    case 11: launch_rb_tile_t<20, 8>(up, t, st); break;
     }
 }
-constexpr int kRbTileChoices = 8;
-constexpr int kRbTileW[kRbTileChoices] = {64, 64, 32, 128, 128, 32, 16, 16}, kRbTileH[kRbTileChoices] = {32, 16, 32, 16, 32, 16, 16, 8};
+constexpr int kRbTileChoices = 12;
+constexpr int kRbTileW[kRbTileChoices] = {64, 64, 32, 128, 128, 32, 16, 16, 52, 52, 20, 20},
+              kRbTileH[kRbTileChoices] = {32, 16, 32, 16, 32, 16, 16, 8, 32, 16, 16, 8};
 template <int TW, int TH>
 cudaError_t rb_tile_set_attr_t()
 {
@@ -167,6 +172,10 @@ cudaError_t rb_tile_set_attr(int choice)
     case 5: return rb_tile_set_attr_t<32, 16>();
     case 6: return rb_tile_set_attr_t<16, 16>();
     case 7: return rb_tile_set_attr_t<16, 8>();
+    case 8: return rb_tile_set_attr_t<52, 32>();
+    case 9: return rb_tile_set_attr_t<52, 16>();
+    case 10: return rb_tile_set_attr_t<20, 16>();
+    case 11: return rb_tile_set_attr_t<20, 8>();
     }
 }
 
@@ -253,14 +262,14 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
     // variant-B tile shape: 32x32 on the latency-bound (L2-resident) levels, 64x32 (less halo redundancy) above -- measured
     auto rb_choice = [&](int l) {
         if (h->rb_tile_choice >= 0) return h->rb_tile_choice;
-        if ((size_t)h->nx[l] * h->ny[l] > 1500000) return 0;
-        const int order[4] = {2, 5, 6, 7};  // 32x32, 32x16, 16x16, 16x8
+        if ((size_t)h->nx[l] * h->ny[l] > 1500000) return 8;
+        const int order[4] = {8, 9, 10, 11};  // 52x32, 52x16, 20x16, 20x8 (row-wise half sweeps)
         for (int k = 0; k < 4; ++k) {
             const int c_ = order[k];
             const long nb = (long)((h->nx[l] + kRbTileW[c_] - 1) / kRbTileW[c_]) * ((h->ny[l] + kRbTileH[c_] - 1) / kRbTileH[c_]);
             if (nb >= h->tile_min_blocks) return c_;
         }
-        return 7;
+        return 11;
     };
     // downward leg on the global-memory levels
     // fuse_sweeps: 1 = automatic (streaming kernels for large levels, where their lower instruction count wins; tile

@@ -89,17 +89,12 @@ __device__ __forceinline__ double rb_half_sweep(double *__restrict__ own, const 
     using Cf = RbCfg<TW, TH, HALO>;
     constexpr int kP2 = Cf::kP2;
     constexpr int w0 = HALO - K, W = TW + 2 * K, H = TH + 2 * K;
-    constexpr int HW = (W + 1) / 2;
+    constexpr int HW = (W + 1) / 2;  // points of one colour per window row (W is even)
     double acc = 0.0;
-    for (int idx = threadIdx.x; idx < H * HW; idx += kTileThreads) {
-        const int rr = idx / HW, kk = idx - rr * HW;
-        const int r = w0 + rr;
-        const int par = (r + X) & 1;                      // parity of the columns of colour X in this row
-        const int c = w0 + ((w0 ^ par) & 1) + 2 * kk;     // kk-th column >= w0 of that parity
-        if (c >= w0 + W) continue;
+    auto point = [&](int r, int c, int par) {
         if (CHECKED) {
             const int i = gx0 + c, j = gy0 + r;
-            if (i < 1 || j < 1 || i > nx - 2 || j > ny - 2) continue;
+            if (i < 1 || j < 1 || i > nx - 2 || j > ny - 2) return;
         }
         const int s = r * kP2 + (c >> 1);
         const double v = own[s];
@@ -111,8 +106,47 @@ __device__ __forceinline__ double rb_half_sweep(double *__restrict__ own, const 
         if (NORM) {
             if (K == 0 || (c >= HALO && c < HALO + TW && r >= HALO && r < HALO + TH)) acc += res * res;
         }
+    };
+    if constexpr (HW <= 32) {
+        // row-wise: a group of LPR lanes owns a window row (no per-point division; parity and row offsets are per row)
+        constexpr int LPR = HW <= 8 ? 8 : (HW <= 16 ? 16 : 32), RPW = 32 / LPR;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int sub = lane / LPR, kk = lane % LPR;
+        if (kk < HW) {
+            for (int rr = warp * RPW + sub; rr < H; rr += (kTileThreads / 32) * RPW) {
+                const int r = w0 + rr;
+                const int par = (r + X) & 1;                   // parity of the columns of colour X in this row
+                point(r, w0 + ((w0 ^ par) & 1) + 2 * kk, par); // kk-th column >= w0 of that parity
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < H * HW; idx += kTileThreads) {
+            const int rr = idx / HW, kk = idx - rr * HW;
+            const int r = w0 + rr;
+            const int par = (r + X) & 1;
+            point(r, w0 + ((w0 ^ par) & 1) + 2 * kk, par);
+        }
     }
     return acc;
+}
+
+// tile proper -> natural-layout global array, one warp per row (coalesced; the two planes are read alternately)
+template <int TW, int TH, int HALO>
+__device__ __forceinline__ void rb_store_tile(const double *__restrict__ UR, const double *__restrict__ UB, double *__restrict__ out,
+                                              int X0, int Y0, int nx, int ny)
+{
+    constexpr int kP2 = RbCfg<TW, TH, HALO>::kP2;
+    for (int r = threadIdx.x >> 5; r < TH; r += kTileThreads / 32) {
+        const int j = Y0 + r;
+        if (j >= ny) continue;
+        const int lr = r + HALO;
+        double *orow = out + (size_t)nx * j + X0;
+        for (int c = threadIdx.x & 31; c < TW; c += 32) {
+            if (X0 + c >= nx) continue;
+            const int lc = c + HALO;
+            orow[c] = (((lc + lr) & 1) ? UB : UR)[lr * kP2 + (lc >> 1)];
+        }
+    }
 }
 
 // the four half sweeps of the downward leg (pre-smoothing: red, black, red, black; the valid window shrinks by one each)
@@ -173,54 +207,57 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_rb_kernel(const TileArgs
     else if (!div) rb_down_sweeps<TW, TH, true, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else rb_down_sweeps<TW, TH, true, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     __syncthreads();
-    // smoothed u out (natural layout, coalesced)
-    for (int idx = threadIdx.x; idx < TW * TH; idx += kTileThreads) {
-        const int r = idx / TW, c = idx - r * TW;
-        const int i = X0 + c, j = Y0 + r;
-        if (i >= nx || j >= ny) continue;
-        const int lc = c + HALO, lr = r + HALO;
-        a.u_out[(size_t)i + (size_t)nx * j] = (((lc + lr) & 1) ? UB : UR)[lr * kP2 + (lc >> 1)];
-    }
+    // smoothed u out (natural layout, coalesced): one warp per tile row
+    rb_store_tile<TW, TH, HALO>(UR, UB, a.u_out, X0, Y0, nx, ny);
     // residual of the smoothed u on tile+1, in place of the right-hand side (multigrid.jl:173-188); interior points only
     // -- the full-weighting stencil of an interior coarse point never reaches the fine frame
     {
-        constexpr int W = TW + 2, H = TH + 2, w0 = HALO - 1;
-        for (int idx = threadIdx.x; idx < W * H; idx += kTileThreads) {
-            const int rr = idx / W, cc = idx - rr * W;
-            const int c = w0 + cc, r = w0 + rr;
-            const int i = gx0 + c, j = gy0 + r;
-            if (i < 1 || j < 1 || i > nx - 2 || j > ny - 2) continue;
-            const int par = (c + r) & 1, cpar = c & 1;
-            const double *own = par ? UB : UR, *oth = par ? UR : UB;
-            double *F = par ? FB : FR;
-            const int s = r * kP2 + (c >> 1);
-            F[s] = ((oth[s + cpar] + oth[s - 1 + cpar] + oth[s + kP2] + oth[s - kP2] - kr.C * own[s]) * kr._h2 - F[s]);
+        constexpr int W = TW + 2, H = TH + 2, w0 = HALO - 1, HW = W / 2;
+        const int lane = threadIdx.x & 31;
+        for (int rr = threadIdx.x >> 5; rr < H; rr += kTileThreads / 32) {
+            const int r = w0 + rr, j = gy0 + r;
+            if (j < 1 || j > ny - 2) continue;
+#pragma unroll
+            for (int X = 0; X < 2; ++X) {
+                const int par = (r + X) & 1;  // column parity of colour X in this row
+                const double *own = X ? UB : UR, *oth = X ? UR : UB;
+                double *F = X ? FB : FR;
+                for (int kk = lane; kk < HW; kk += 32) {
+                    const int c = w0 + ((w0 ^ par) & 1) + 2 * kk, i = gx0 + c;
+                    if (i < 1 || i > nx - 2) continue;
+                    const int s = r * kP2 + (c >> 1);
+                    F[s] = ((oth[s + par] + oth[s - 1 + par] + oth[s + kP2] + oth[s - kP2] - kr.C * own[s]) * kr._h2 - F[s]);
+                }
+            }
         }
     }
     __syncthreads();
-    // coarse rhs = full weighting of the residual (+ Neumann copies), coarse unknown = 0
+    // coarse rhs = full weighting of the residual (+ Neumann copies), coarse unknown = 0: one warp per coarse row
     const int nxc = a.nxc, nyc = a.nyc;
-    for (int idx = threadIdx.x; idx < (TW / 2) * (TH / 2); idx += kTileThreads) {
-        const int rr = idx / (TW / 2), cc = idx - rr * (TW / 2);
-        const int I = X0 / 2 + cc, J = Y0 / 2 + rr;
-        if (I >= nxc || J >= nyc) continue;
-        const size_t pc = (size_t)I + (size_t)nxc * J;
-        a.ec[pc] = 0.0;
-        const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
-        if (interior) {
-            // fine point (2I, 2J): local (even, even) -> red plane; its x neighbours are black at m-1, m; the diagonal
-            // neighbours are red at m-1, m of the rows below and above
-            const int s = (2 * rr + HALO) * kP2 + (cc + HALO / 2);
-            const double corners = (FR[s - kP2 - 1] + FR[s - kP2]) + (FR[s + kP2 - 1] + FR[s + kP2]);
-            const double edges = (FB[s - 1] + FB[s]) + (FB[s - kP2] + FB[s + kP2]);
-            const double v = ((corners + 2.0 * edges) + 4.0 * FR[s]) * 0.0625;
-            a.rc[pc] = v;
-            if (apply_bcs) {  // coarse[0,:] = coarse[1,:] ; coarse[nxc-1,:] = coarse[nxc-2,:]
-                if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
-                if (I == nxc - 2) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+    for (int rr = threadIdx.x >> 5; rr < TH / 2; rr += kTileThreads / 32) {
+        const int J = Y0 / 2 + rr;
+        if (J >= nyc) continue;
+        const bool jint = J >= 1 && J <= nyc - 2;
+        for (int cc = threadIdx.x & 31; cc < TW / 2; cc += 32) {
+            const int I = X0 / 2 + cc;
+            if (I >= nxc) continue;
+            const size_t pc = (size_t)I + (size_t)nxc * J;
+            a.ec[pc] = 0.0;
+            if (jint && I >= 1 && I <= nxc - 2) {
+                // fine point (2I, 2J): local (even, even) -> red plane; its x neighbours are black at m-1, m; the diagonal
+                // neighbours are red at m-1, m of the rows below and above
+                const int s = (2 * rr + HALO) * kP2 + (cc + HALO / 2);
+                const double corners = (FR[s - kP2 - 1] + FR[s - kP2]) + (FR[s + kP2 - 1] + FR[s + kP2]);
+                const double edges = (FB[s - 1] + FB[s]) + (FB[s - kP2] + FB[s + kP2]);
+                const double v = ((corners + 2.0 * edges) + 4.0 * FR[s]) * 0.0625;
+                a.rc[pc] = v;
+                if (apply_bcs) {  // coarse[0,:] = coarse[1,:] ; coarse[nxc-1,:] = coarse[nxc-2,:]
+                    if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
+                    if (I == nxc - 2) a.rc[(size_t)(nxc - 1) + (size_t)nxc * J] = v;
+                }
+            } else if (!(apply_bcs && (I == 0 || I == nxc - 1) && jint)) {
+                a.rc[pc] = 0.0;
             }
-        } else if (!(apply_bcs && (I == 0 || I == nxc - 1) && J >= 1 && J <= nyc - 2)) {
-            a.rc[pc] = 0.0;
         }
     }
 }
@@ -247,21 +284,32 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
     const int cx0 = X0 / 2 - 2, cy0 = Y0 / 2 - 2;
     rb_stage<kW, kRows, kP2>(UR, UB, a.u_in, gx0, gy0, nx, ny, 0, kW, 0, kRows);
     rb_stage<kW, kRows, kP2>(FR, FB, rhs, gx0, gy0, nx, ny, 1, kW - 1, 1, kRows - 1);
-    for (int idx = threadIdx.x; idx < kCW * kCH; idx += kTileThreads) {
-        const int r = idx / kCW, c = idx - r * kCW;
-        const int I = cx0 + c, J = cy0 + r;
-        const bool in = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;  // the boundary ring counts as 0
-        cp_async8(Cw + idx, a.ec + (in ? (size_t)I + (size_t)nxc * J : 0), in);
+    for (int r = threadIdx.x >> 5; r < kCH; r += kTileThreads / 32) {
+        const int J = cy0 + r;
+        const bool jin = J >= 1 && J <= nyc - 2;  // the boundary ring counts as 0
+        const size_t rowoff = jin ? (size_t)nxc * J : 0;
+        for (int c = threadIdx.x & 31; c < kCW; c += 32) {
+            const int I = cx0 + c;
+            const bool in = jin && I >= 1 && I <= nxc - 2;
+            cp_async8(Cw + r * kCW + c, a.ec + (in ? rowoff + I : 0), in);
+        }
     }
     cp_async_wait_all();
     __syncthreads();
-    // u_f .= u_f - corr_f on tile+4 (multigrid.jl:136-139)
-    for (int idx = threadIdx.x; idx < kW * kRows; idx += kTileThreads) {
-        const int r = idx / kW, c = idx - r * kW;
-        const int i = gx0 + c, j = gy0 + r;
-        if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
-        double *p = (((c + r) & 1) ? UB : UR) + r * kP2 + (c >> 1);
-        *p = *p - prolong_from_window<kCW>(Cw, cx0, cy0, nx, i, j, apply_bcs);
+    // u_f .= u_f - corr_f on tile+4 (multigrid.jl:136-139): one warp per staged row, one column parity per pass (the
+    // interpolation formula and the colour plane are then uniform across the warp)
+    for (int r = threadIdx.x >> 5; r < kRows; r += kTileThreads / 32) {
+        const int j = gy0 + r;
+        if (j < 0 || j >= ny) continue;
+#pragma unroll
+        for (int cpar = 0; cpar < 2; ++cpar) {
+            double *row = (((cpar + r) & 1) ? UB : UR) + r * kP2;
+            for (int m = threadIdx.x & 31; 2 * m + cpar < kW; m += 32) {
+                const int i = gx0 + 2 * m + cpar;
+                if (i < 0 || i >= nx) continue;
+                row[m] = row[m] - prolong_from_window<kCW>(Cw, cx0, cy0, nx, i, j, apply_bcs);
+            }
+        }
     }
     __syncthreads();
     const bool inner = X0 - 3 >= 1 && Y0 - 3 >= 1 && X0 + TW + 2 <= nx - 2 && Y0 + TH + 2 <= ny - 2;
@@ -272,13 +320,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
     else if (!div) acc = rb_up_sweeps<TW, TH, true, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else acc = rb_up_sweeps<TW, TH, true, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < TW * TH; idx += kTileThreads) {
-        const int r = idx / TW, c = idx - r * TW;
-        const int i = X0 + c, j = Y0 + r;
-        if (i >= nx || j >= ny) continue;
-        const int lc = c + HALO, lr = r + HALO;
-        out[(size_t)i + (size_t)nx * j] = (((lc + lr) & 1) ? UB : UR)[lr * kP2 + (lc >> 1)];
-    }
+    rb_store_tile<TW, TH, HALO>(UR, UB, out, X0, Y0, nx, ny);
     if (a.want_norm) {
         const int nblocks = gridDim.x * gridDim.y;
         const int bl = blockIdx.x + gridDim.x * blockIdx.y;
