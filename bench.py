@@ -141,6 +141,12 @@ def cpu_reference_run(n, seconds, threads=None):
                       f"OpenMP oracle port of the reference's Threads path, {O.num_threads()} threads"}, iters, dt
 
 
+def workload_name(n, N, iters):
+    return (f"3D pseudo-transient diffusion {n}^3 Float64 per GPU (part1_benchmark.jl shape; "
+            f"BASELINE configs[2]{' / configs[4] weak scaling, z-slabs' if N > 1 else ''}), "
+            f"{iters} PT iterations per step, Gaussian initial condition")
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -165,8 +171,11 @@ def run_reference(args, rank):
     out = {"impl": "reference", "metric": "diffusion3d_T_eff", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"3D pseudo-transient diffusion {n}^3 Float64 (part1_benchmark.jl shape), "
-                                  f"{iters} PT iterations per step", "iters_per_step": iters},
+           # the same workload as the CUDA arm's config (512^3 per GPU, args.iters PT iterations per step); one reference
+           # step is a bounded sample of it (`sample_iters_per_step` iterations), the metric is a rate and does not depend on it
+           "config": {"workload": workload_name(n, args.gpus, args.iters), "iters_per_step": args.iters,
+                      "sample_iters_per_step": iters, "local_grid": [n, n, n], "dims": [1, 1, 1],
+                      "note": "CPU path on rank 0 only: one rank's grid"},
            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -354,9 +363,7 @@ def _finish(args, rank, N, n, dev, peak, value, ms_per_step, wall, roofline, e2e
         out = {"metric": "diffusion3d_T_eff", "value": value, "unit": "GB/s", "n_gpus": N, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": f"3D pseudo-transient diffusion {n}^3 Float64 per GPU (part1_benchmark.jl shape; "
-                                      f"BASELINE configs[2]{' / configs[4] weak scaling, z-slabs' if N > 1 else ''}), "
-                                      f"{iters} PT iterations per step, Gaussian initial condition",
+               "config": {"workload": workload_name(n, N, iters),
                           "iters_per_step": iters, "local_grid": [n, n, n], "dims": [1, 1, N],
                           "halo_mode": "reference_lag2", "l2": "inputs (3 GiB of fields per GPU) larger than L2",
                           "kernel_variant": args.variant, "timing": "CUDA events inside the library on its stream, "
