@@ -387,6 +387,27 @@ def test_error_conditions(p2):
     assert r > 0
 
 
+def test_variant_b_full_size_properties(p2):
+    """Variant B at sizes the oracle cannot visit in seconds: the fused kernels (colour-split shared-memory planes) and
+    the one-kernel-per-half-sweep path must agree bit for bit, need the same 5 V-cycles and contract the residual by
+    more than 10x per cycle."""
+    n = 2049
+    h = 1.0 / (n - 1)
+    b = p2.to_device(rnd((n, n), 7))
+    res = {}
+    for fuse in (True, False):
+        x = p2.zeros(n, n)
+        hd = p2.preallocate_buffers(n, n, p2.MGOpt(smoother=1, restriction=1, fuse_sweeps=fuse))
+        r, nc, hist = hd.solve(x, b, h, 0.0, 1e-6, 30, False, want_hist=True)
+        res[fuse] = (p2.to_host(x), nc, hist)
+        hd.close()
+    assert res[True][1] == res[False][1] == 5
+    assert np.array_equal(res[True][0], res[False][0])
+    hist = res[True][2]
+    assert all(hist[i + 1] < 0.1 * hist[i] for i in range(len(hist) - 1))
+    assert np.allclose(res[True][2], res[False][2], rtol=1e-9, atol=0)
+
+
 def test_full_size_properties(p2):
     """2049^2 (config #4 grid) and 4097^2: graph replay == plain launches bit-for-bit, 7 V-cycles, converged."""
     for n in (2049, 4097):
