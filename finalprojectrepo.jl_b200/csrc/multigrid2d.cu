@@ -498,9 +498,22 @@ int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count)
         const int rows = rows_for(nx, ny);
         int launched = 0;
         CoarseLoop cur = {};
+        const bool rb = h->cfg.smoother == B2S_SMOOTH_RBGS;
         while (!cur.done) {
             const int batch = std::min(32, iters - launched);
-            for (int k = 0; k < batch; ++k, ++launched) {
+            for (int k = 0; k < batch && rb; ++k, ++launched) {  // red-black Gauss-Seidel sweeps, in place
+                for (int colour = 0; colour < 2; ++colour) {
+                    RbgsArgs a = {};
+                    a.u = u; a.rhs = rhs; a.nx = nx; a.ny = ny; a.rows = rows; a.colour = colour; a.h = hl; a.c = m.c;
+                    a.want_norm = 1; a.partials = h->partials; a.ticket = h->ticket; a.sumsq_out = h->sumsq_dev + 2;
+                    a.loop = h->loop_dev;
+                    dim3 g(((nx + 1) / 2 + kMGBX - 1) / kMGBX, (ny + rows - 1) / rows, 1);
+                    mg_rbgs_kernel<<<g, kMGBX, 0, st>>>(a);
+                }
+                mg_coarse_loop_rb_step_kernel<<<1, 32, 0, st>>>(h->loop_dev, h->sumsq_dev);
+                nl += 3;
+            }
+            for (int k = 0; k < batch && !rb; ++k, ++launched) {
                 SweepArgs a = {};
                 a.nx = nx; a.ny = ny; a.rows = rows; a.h = hl; a.c = m.c; a.alpha = 4.0 / 5.0; a.mode = 1;
                 a.rhs = rhs;
@@ -518,7 +531,7 @@ int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count)
             launched = cur.sweeps;  // launches after the exit were no-ops
             if (launched >= iters) break;
         }
-        if (cur.sweeps & 1)  // odd number of sweeps: the result sits in tmp
+        if (!rb && (cur.sweeps & 1))  // odd number of Jacobi sweeps: the result sits in tmp
             B2S_CUDA(cudaMemcpyAsync(u, h->tmp[l], n * sizeof(double), cudaMemcpyDeviceToDevice, st));
         h->last_sweeps_host = cur.sweeps;
     }
@@ -691,12 +704,6 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
             fs = l;
         }
         if (fs == L) {  // coarsest level does not fit into shared memory: global-memory coarsest solve, host-polled
-            if (cfg->smoother == B2S_SMOOTH_RBGS && cfg->coarse_solver == B2S_COARSE_JACOBI) {
-                set_error("coarsest level %dx%d with the red-black smoother does not fit into shared memory (not implemented)",
-                          h->nx[L - 1], h->ny[L - 1]);
-                delete h;
-                return B2S_ERR_NOT_IMPLEMENTED;
-            }
             h->coarse_global = true;
             h->cfg.use_graph = 0;  // the coarsest solve polls the device between batches of sweeps
             bytes = 0;

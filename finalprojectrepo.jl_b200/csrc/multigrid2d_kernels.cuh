@@ -220,11 +220,13 @@ struct RbgsArgs {
     double *partials;
     unsigned int *ticket;
     double *sumsq_out;
+    const CoarseLoop *loop;  // nullable: global-memory coarsest solve -- skip when its exit test has fired
 };
 
 __global__ void __launch_bounds__(kMGBX) mg_rbgs_kernel(const RbgsArgs a)
 {
     __shared__ double red[32];
+    if (a.loop != nullptr && a.loop->done) return;
     if (a.cp != nullptr && a.cp->done) return;
     double *u = a.u;
     const double *rhs = a.rhs;
@@ -2175,6 +2177,18 @@ __global__ void mg_coarse_loop_init_kernel(CoarseLoop *loop, const double *sumsq
         loop->done = 0;
         loop->iters = iters;
     }
+}
+
+// One red-black sweep of a global-memory coarsest solve is done (two mg_rbgs_kernel launches): res_rms < tol_rhs -> break
+// (multigrid.jl:150-156) with sum res^2 = red + black.
+__global__ void mg_coarse_loop_rb_step_kernel(CoarseLoop *loop, double *sumsq)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || loop->done) return;
+    const double total = sumsq[2] + sumsq[3];
+    sumsq[0] = total;
+    const int sw = loop->sweeps + 1;
+    loop->sweeps = sw;
+    if (total < loop->sstar || sw >= loop->iters) loop->done = 1;
 }
 
 // Stand-alone CG for grids that fit into shared memory (test/krylov.jl shape: 66^2).

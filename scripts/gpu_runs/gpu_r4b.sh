@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_multigrid.py -m gpu -q -x > gpurun_out/r4b_pytest_mg.log 2>&1
+echo "pytest exit $?" >> gpurun_out/r4b_pytest_mg.log
+true

@@ -217,6 +217,26 @@ def test_large_coarsest_level_in_global_memory(p2, oracle, solver):
     hd.close()
 
 
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "unfused"])
+def test_large_coarsest_level_red_black(p2, oracle, fuse):
+    """Variant B with a coarsest level that does not fit into shared memory (129^2): red-black Gauss-Seidel sweeps in
+    global memory with the exit test on the device; same sweep counts, V-cycle count and bits as the oracle."""
+    n, cs = 257, 129
+    h = 1.0 / (n - 1)
+    b = rnd((n, n), 3)
+    opt_o = oracle.MGOpt(coarse_solve_size=cs, smoother=1, restriction=1)
+    xo = oracle.farray((n, n))
+    r_o, nc_o, hist_o = oracle.mgsolve2d(xo, b, h, 0.0, 1e-6, 20, opt=opt_o)
+    sw_o = oracle.lib().orc_mg_last_coarse_sweeps()
+    x = p2.zeros(n, n)
+    hd = p2.preallocate_buffers(n, n, p2.MGOpt(coarse_solve_size=cs, smoother=1, restriction=1, fuse_sweeps=fuse))
+    r_g, nc_g, hist_g = hd.solve(x, p2.to_device(b), h, 0.0, 1e-6, 20, False, want_hist=True)
+    assert nc_g == nc_o and hd.last_coarse_sweeps() == sw_o
+    assert np.allclose(hist_g, hist_o, rtol=1e-9, atol=0)
+    assert np.array_equal(p2.to_host(x), xo)
+    hd.close()
+
+
 def test_cg_larger_than_shared_memory(p2, oracle):
     n, c = 130, 3.14
     h = 1.0 / (n - 1)
