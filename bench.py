@@ -198,6 +198,10 @@ def mg_bench(device, peak):
     except Exception as e:  # pragma: no cover
         out["variant_b_rbgs_fw"] = {"unavailable": f"{type(e).__name__}: {e}"}
     try:
+        out["config2_matrix_1025"] = part2.bench_config2_matrix(device=device, n=1025)
+    except Exception as e:  # pragma: no cover
+        out["config2_matrix_1025"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    try:
         out["navier_stokes_2049"] = part2.bench_navier_stokes(device=device)
     except Exception as e:  # pragma: no cover
         out["navier_stokes_2049"] = {"unavailable": f"{type(e).__name__}: {e}"}

@@ -1842,54 +1842,94 @@ struct WarpPoints {
             interior[m] = valid[m] && i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
         }
     }
+    // Branch-free (frame points evaluate the stencil at a safe interior index and discard it), so that the M dependent
+    // chains of a lane overlap instead of running one after the other in separate divergent regions.
     __device__ __forceinline__ double sweep(const double *src, const double *rhs, double *dst, int nx, const Coef &k) const
     {
         double acc = 0.0;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            if (interior[m]) {
-                const int q = p[m];
-                const double r = ((src[q + 1] + src[q - 1] + src[q + nx] + src[q - nx] - k.C * src[q]) * k._h2 - rhs[q]);
-                acc += r * r;
-                dst[q] = src[q] + k.w * r;
-            } else if (valid[m]) {
-                dst[p[m]] = src[p[m]];
-            }
+            const int q = interior[m] ? p[m] : nx + 1;
+            const double own = valid[m] ? src[p[m]] : 0.0;
+            const double r = ((src[q + 1] + src[q - 1] + src[q + nx] + src[q - nx] - k.C * src[q]) * k._h2 - rhs[q]);
+            const double vn = src[q] + k.w * r;
+            acc += interior[m] ? r * r : 0.0;
+            if (valid[m]) dst[p[m]] = interior[m] ? vn : own;
         }
         return acc;
     }
 };
 
-// Coarsest Jacobi solve in one warp, software-pipelined: sweep s+1 is computed speculatively (into the other
-// ping-pong buffer) while the residual norm of sweep s is still being reduced; if sweep s satisfied the exit test its
-// result is simply kept. Returns sum res^2 of the last counted sweep; the solution ends up in u.
-template <int M>
-__device__ __forceinline__ double warp_coarsest_jacobi(double *u, const double *rhs, double *tmp, int nx, int ny, const Coef &k,
-                                                       double sstar, int iters, int *sweeps_out)
+// Reduction of the per-lane res^2 of the (up to 8) sweeps of a batch, stored as accbuf[sweep][lane] by the whole warp:
+// lanes 4b..4b+3 sum sweep b (8 loads and a 3-level add tree each, then 2 shuffle levels). Returns in every lane the
+// index of the first sweep b < nb whose total is below sstar (-1: none) and, through tot_of_hit, that total (or the
+// total of sweep nb-1 when none passes). All 32 lanes must call.
+__device__ __forceinline__ int batch_first_hit(const double (*accbuf)[32], int nb, double sstar, double *tot_of_hit)
 {
+    const int lane = threadIdx.x & 31, rb = lane >> 2, rp = (lane & 3) * 8;
+    const double *q = &accbuf[rb][rp];
+    double t = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    const unsigned ok = __ballot_sync(0xffffffffu, rb < nb && t < sstar);
+    const int hit = ok ? ((__ffs(ok) - 1) >> 2) : -1;
+    *tot_of_hit = __shfl_sync(0xffffffffu, t, 4 * (hit >= 0 ? hit : nb - 1));
+    return hit;
+}
+
+// Coarsest Jacobi solve of a grid with 33..128 points in one warp (M points per lane, state in two shared-memory
+// buffers). Like the register version below, the exit test of the reference (res_rms < tol_rhs after every sweep,
+// multigrid.jl:150-156) is taken off the dependent chain: sweeps run speculatively in batches of 8, each sweep stores its
+// per-lane res^2, one reduction per batch finds the first sweep that passes; the state at the start of the batch is kept
+// in registers, and if the batch ran past the exit it is restored and the counted sweeps are redone (identical
+// arithmetic). Returns sum res^2 of the last counted sweep; the solution ends up in u.
+template <int M>
+__device__ __noinline__ double warp_coarsest_jacobi(double *u, const double *rhs, double *tmp, int nx, int ny, const Coef &kref,
+                                                    double sstar, int iters, int *sweeps_out)
+{
+    __shared__ double accbuf[8][32];
+    const Coef k = kref;
     const WarpPoints<M> wp(nx, ny);
-    const int n = nx * ny;
+    const int n = nx * ny, lane = threadIdx.x & 31;
     double *cur = u, *oth = tmp;
-    double acc = wp.sweep(cur, rhs, oth, nx, k);  // sweep 1: u -> tmp
-    __syncwarp();
-    { double *t_ = cur; cur = oth; oth = t_; }
     double tot = 0.0;
-    int s = 1;
-    for (;; ++s) {
-        double acc_next = 0.0;
-        if (s < iters) acc_next = wp.sweep(cur, rhs, oth, nx, k);  // speculative sweep s+1
-        tot = warp_sum(acc);
-        if (tot < sstar || s >= iters) break;
+    int s = 0;
+    for (;;) {
+        double snap[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) snap[m] = wp.valid[m] ? cur[wp.p[m]] : 0.0;
+        double *const start = cur;
+        const int nb = min(8, iters - s);
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            accbuf[b][lane] = wp.sweep(cur, rhs, oth, nx, k);
+            __syncwarp();
+            double *t_ = cur; cur = oth; oth = t_;
+        }
+        const int hit = batch_first_hit(accbuf, nb, sstar, &tot);
         __syncwarp();
-        { double *t_ = cur; cur = oth; oth = t_; }
-        acc = acc_next;
+        if (hit < 0 && s + nb < iters) { s += nb; continue; }
+        const int last = hit >= 0 ? hit : nb - 1;  // the cap 20*coarse_solve_size ends the loop otherwise
+        if (last != nb - 1) {  // the batch ran past the exit: restore its start state and redo the counted sweeps
+            cur = start; oth = (start == u) ? tmp : u;
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (wp.valid[m]) cur[wp.p[m]] = snap[m];
+            __syncwarp();
+            for (int b = 0; b <= last; ++b) {
+                wp.sweep(cur, rhs, oth, nx, k);
+                __syncwarp();
+                double *t_ = cur; cur = oth; oth = t_;
+            }
+        }
+        s += last + 1;
+        break;
     }
-    __syncwarp();
     if (cur != u) {
-        for (int q = threadIdx.x & 31; q < n; q += 32) u[q] = cur[q];
+        for (int q = lane; q < n; q += 32) u[q] = cur[q];
         __syncwarp();
     }
-    if (sweeps_out != nullptr && (threadIdx.x & 31) == 0) *sweeps_out = s;
+    if (sweeps_out != nullptr && lane == 0) *sweeps_out = s;
     return tot;
 }
 
@@ -1965,7 +2005,6 @@ __device__ __noinline__ double warp_coarsest_reg(double *u, const double *rhs, i
         sw.C = k.C; sw.s2 = k._h2; sw.kw = k.w;
     }
     double v = valid ? u[lane] : 0.0;
-    const int rb = lane >> 2, rp = (lane & 3) * 8;  // reduction: lanes 4b..4b+3 sum sweep b, 8 lanes' worth each
     double tot = 0.0;
     int s = 0;
     for (;;) {
@@ -1994,16 +2033,10 @@ __device__ __noinline__ double warp_coarsest_reg(double *u, const double *rhs, i
         if (nst < 60) s_stamps[nst++] = clock64();
 #endif
         __syncwarp();
-        const double *q = &accbuf[rb][rp];
-        double t = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
-        const unsigned ok = __ballot_sync(0xffffffffu, rb < nb && t < sstar);
+        int hit = batch_first_hit(accbuf, nb, sstar, &tot);  // first sweep of the batch that passes res_rms < tol_rhs
         __syncwarp();
-        int hit = ok ? ((__ffs(ok) - 1) >> 2) : -1;  // first sweep of the batch that passes res_rms < tol_rhs
         if (hit < 0 && s + nb < iters) { s += nb; continue; }
         if (hit < 0) hit = nb - 1;  // the cap 20*coarse_solve_size ends the loop
-        tot = __shfl_sync(0xffffffffu, t, 4 * hit);
         v = vbuf[hit][lane];  // state after the last counted sweep
         s += hit + 1;
         break;

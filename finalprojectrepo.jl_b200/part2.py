@@ -386,7 +386,7 @@ def mg_fused_min_bytes(nx, ny, coarse_solve_size=5):
     return mg_algorithmic_bytes(nx, ny, coarse_solve_size) / 132.0 * 54.0
 
 
-def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycles=50, seed=1, opt=None):
+def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycles=50, seed=1, opt=None, e2e=True):
     """Config #2 (multigrid_bench.jl shape): x = 0, b ~ U[0,1) on all entries, c = 0, tol 1e-6; DoF/s per V-cycle with
     fields resident on the device (CUDA events inside the library), plus the whole-solve time and cycle count."""
     torch = _torch()
@@ -413,7 +413,7 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
         b_host = torch.from_numpy(np.ascontiguousarray(np.random.default_rng(seed).random((n, n)).T)).pin_memory()
         x_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
         e2e_s = float("inf")
-        for _ in range(3):
+        for _ in range(3 if e2e else 0):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             bd = b_host.to(f"cuda:{device}", non_blocking=True).T
@@ -437,6 +437,22 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
                                 "kernel_launches_per_vcycle": (l1 - l0) / ncycles}
         hd.close()
     return out
+
+
+def bench_config2_matrix(device=0, n=1025, ncycles=30):
+    """Config #2 as multigrid_bench.jl sweeps it: coarse_solve_size in {5, 9} x coarse solver {Jacobi, CG} for variant A
+    (damped Jacobi + injection) and variant B (red-black Gauss-Seidel + full weighting): ms per V-cycle, V-cycles to 1e-6."""
+    rows = []
+    for variant in ("A", "B"):
+        for cs in (5, 9):
+            for solver in (jacobi, conjugate_gradient):
+                opt = MGOpt(coarse_solve_size=cs, coarse_solver=solver, smoother=1 if variant == "B" else 0,
+                            restriction=1 if variant == "B" else 0)
+                d = bench_vcycle(device=device, sizes=(n,), ncycles=ncycles, opt=opt, e2e=False)["sizes"][str(n)]
+                rows.append({"variant": variant, "coarse_solve_size": cs, "coarse_solver": "jacobi" if solver == jacobi else "cg",
+                             "ms_per_vcycle": d["ms_per_vcycle"], "dof_per_s": d["dof_per_s"], "vcycles_to_1e-6": d["vcycles_to_1e-6"],
+                             "solve_ms": d["solve_ms"]})
+    return rows
 
 
 def bench_navier_stokes(device=0, n=2049, steps=8, seed=1):
