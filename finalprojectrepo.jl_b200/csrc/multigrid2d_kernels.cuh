@@ -1830,7 +1830,7 @@ __device__ __forceinline__ double exit_threshold(double T, double N)
 template <int M>
 struct WarpPoints {
     int p[M];
-    bool valid[M], interior[M];
+    bool valid[M], interior[M], red[M];
     __device__ __forceinline__ WarpPoints(int nx, int ny)
     {
         const int lane = threadIdx.x & 31, n = nx * ny;
@@ -1840,6 +1840,7 @@ struct WarpPoints {
             valid[m] = p[m] < n;
             const int j = p[m] / nx, i = p[m] - j * nx;
             interior[m] = valid[m] && i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
+            red[m] = ((i + j) & 1) == 0;
         }
     }
     // Branch-free (frame points evaluate the stencil at a safe interior index and discard it), so that the M dependent
@@ -1855,6 +1856,26 @@ struct WarpPoints {
             const double vn = src[q] + k.w * r;
             acc += interior[m] ? r * r : 0.0;
             if (valid[m]) dst[p[m]] = interior[m] ? vn : own;
+        }
+        return acc;
+    }
+    // One red-black Gauss-Seidel sweep in place (variant B): red half step, __syncwarp, black half step; returns this
+    // lane's share of the pre-update res^2 of both colours. Same branch-free scheme.
+    __device__ __forceinline__ double sweep_rb(double *u, const double *rhs, int nx, double C, double w, const DivH2 &dh) const
+    {
+        double acc = 0.0;
+#pragma unroll
+        for (int colour = 0; colour < 2; ++colour) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const bool act = interior[m] && red[m] == (colour == 0);
+                const int q = act ? p[m] : nx + 1;
+                const double r = div_h2(u[q + 1] + u[q - 1] + u[q + nx] + u[q - nx] - C * u[q], dh) - rhs[q];
+                const double vn = u[q] + w * r;
+                acc += act ? r * r : 0.0;
+                if (act) u[p[m]] = vn;
+            }
+            __syncwarp();
         }
         return acc;
     }
@@ -1928,6 +1949,44 @@ __device__ __noinline__ double warp_coarsest_jacobi(double *u, const double *rhs
     if (cur != u) {
         for (int q = lane; q < n; q += 32) u[q] = cur[q];
         __syncwarp();
+    }
+    if (sweeps_out != nullptr && lane == 0) *sweeps_out = s;
+    return tot;
+}
+
+// The same for the red-black Gauss-Seidel smoother (variant B; sweeps are in place, so there is no second buffer).
+template <int M>
+__device__ __noinline__ double warp_coarsest_rbgs(double *u, const double *rhs, int nx, int ny, double h, double c, double sstar,
+                                                  int iters, int *sweeps_out)
+{
+    __shared__ double accbuf[8][32];
+    const WarpPoints<M> wp(nx, ny);
+    const int lane = threadIdx.x & 31;
+    const double C = 4.0 + c * (h * h), w = 1.0 * ((h * h) / C);
+    const DivH2 dh = make_div_h2(h * h);
+    double tot = 0.0;
+    int s = 0;
+    for (;;) {
+        double snap[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) snap[m] = wp.valid[m] ? u[wp.p[m]] : 0.0;
+        const int nb = min(8, iters - s);
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) accbuf[b][lane] = wp.sweep_rb(u, rhs, nx, C, w, dh);
+        __syncwarp();
+        const int hit = batch_first_hit(accbuf, nb, sstar, &tot);
+        __syncwarp();
+        if (hit < 0 && s + nb < iters) { s += nb; continue; }
+        const int last = hit >= 0 ? hit : nb - 1;
+        if (last != nb - 1) {  // the batch ran past the exit: restore its start state and redo the counted sweeps
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (wp.valid[m]) u[wp.p[m]] = snap[m];
+            __syncwarp();
+            for (int b = 0; b <= last; ++b) wp.sweep_rb(u, rhs, nx, C, w, dh);
+        }
+        s += last + 1;
+        break;
     }
     if (sweeps_out != nullptr && lane == 0) *sweeps_out = s;
     return tot;
@@ -2066,6 +2125,11 @@ __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const doubl
         if (g.size() == 32 && n <= 32 && nx >= 3) {  // register-resident solve (shuffles wrap correctly only for nx >= 2)
             if (a.smoother == B2S_SMOOTH_RBGS) return warp_coarsest_reg<true>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
             return warp_coarsest_reg<false>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
+        }
+        if (a.smoother == B2S_SMOOTH_RBGS && g.size() == 32 && n <= 128 && nx >= 3 && ny >= 3) {
+            if (n <= 64) return warp_coarsest_rbgs<2>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
+            if (n <= 96) return warp_coarsest_rbgs<3>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
+            return warp_coarsest_rbgs<4>(u, rhs, nx, ny, h, c, sstar, iters, sweeps_out);
         }
         if (a.smoother == B2S_SMOOTH_JACOBI && g.size() == 32 && n <= 128) {
             if (n <= 32) return warp_coarsest_jacobi<1>(u, rhs, tmp, nx, ny, k, sstar, iters, sweeps_out);

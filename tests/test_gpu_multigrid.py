@@ -116,6 +116,8 @@ CONFIGS = [
     dict(smoother=1, restriction=1),                    # variant B: RB-GS + full weighting (fused tile kernels)
     dict(smoother=1, restriction=1, fuse_sweeps=False), # variant B, one kernel per half sweep / transfer operator
     dict(smoother=1, restriction=1, use_graph=False, smem_levels=False),
+    dict(smoother=1, restriction=1, coarse_solve_size=9),  # 9x9 coarsest grid: in-warp red-black solve, 3 points per lane
+    dict(smoother=1, restriction=1, coarse_solve_size=3),  # 3x3 coarsest grid
 ]
 
 
