@@ -171,7 +171,7 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Arena {  // layout of the per-slab device allocation (identical on every rank -> usable through IPC)
-    size_t cells, off_ht, off_buf[2], off_slots, off_state, off_partials, off_ticket, off_peer_table, bytes;
+    size_t cells, off_ht, off_buf[2], off_slots, off_state, off_partials, off_ticket, off_peer_table, off_cart, off_cart_table, bytes;
     void layout(size_t ncells)
     {
         cells = ncells;
@@ -185,6 +185,8 @@ struct Arena {  // layout of the per-slab device allocation (identical on every 
         off_partials = o; o += align_up(sizeof(double) * kMaxPartials, 1024);
         off_ticket = o; o += 1024;
         off_peer_table = o; o += align_up(sizeof(void *) * kMaxRanks, 1024);
+        off_cart = o; o += align_up(sizeof(CartSync), 1024);
+        off_cart_table = o; o += align_up(sizeof(void *) * kMaxRanks, 1024);
         bytes = o;
     }
 };
@@ -232,6 +234,7 @@ struct b2s_diff3d {
     int nslots_dst = 0;           // RankSlots instances that receive partials (devices in-process, ranks multi-process)
     bool multi = false;           // more than one slab in the global stack
     bool cart = false;            // decomposition in x or y as well: update_halo! as separate plane copies
+    std::vector<char *> peer_base; // one process per GPU: every rank's arena (own or IPC-mapped), in rank order
     bool connected = false;       // multi-process: peers mapped
     std::vector<void *> ipc_mapped;
     long long launched = 0;       // PT iterations since create (host mirror of PTState::total_iters)
@@ -295,8 +298,55 @@ int cross_device_barrier(b2s_diff3d *h)
 // goes to the high rank's plane 0 and the high rank's plane 1 to the low rank's plane n-1 (whole planes, overlap 2).
 // The reference exchanges the buffer the step kernel has just READ (part1_kernel_programming.jl:182,187: halos lag two
 // iterations) -- `which` selects it; the consistent mode passes the buffer just written.
+// The same for one process per GPU: this rank PULLS the two planes of every split axis from its neighbours' arenas
+// (CUDA IPC mappings over NVLink); the phases are separated by cart_barrier_kernel instead of events.
+int cart_update_halo_multiprocess(b2s_diff3d *h, int which)
+{
+    const b2s_diff3d_config &c = h->cfg;
+    int dims[3], coord[3];
+    cart_dims(c, dims);
+    Slab &me = h->slabs[0];
+    DeviceCtx &d = h->devs[me.devslot];
+    cart_coords(c, me.rank, coord);
+    const int nd[3] = {c.nx, c.ny, c.nz};
+    CartSync *mine = (CartSync *)(me.arena + h->ar.off_cart);
+    CartSync *const *table = (CartSync *const *)(me.arena + h->ar.off_cart_table);
+    int k = 1;
+    auto barrier = [&]() {
+        cart_barrier_kernel<<<1, kMaxRanks, 0, d.stream>>>(d.state, mine, table, c.nslabs_total, me.rank, k++, (long long)20e9);
+        h->kernel_launches += 1;
+    };
+    auto peer_buf = [&](const int cc[3]) {
+        const int r = (cc[0] * dims[1] + cc[1]) * dims[2] + cc[2];
+        return (double *)(h->peer_base[(size_t)r] + h->ar.off_buf[which]);
+    };
+    barrier();  // every rank's step kernel is done before anyone's halo cells change
+    for (int axis = 0; axis < 3; ++axis) {
+        if (dims[axis] == 1) continue;
+        const size_t plane = (size_t)nd[(axis + 1) % 3] * nd[(axis + 2) % 3];
+        const int blocks = (int)std::min<size_t>((plane + 255) / 256, 592);
+        const int n = nd[axis];
+        if (coord[axis] > 0) {  // low neighbour's plane n-2 -> my plane 0
+            int cc[3] = {coord[0], coord[1], coord[2]};
+            cc[axis] -= 1;
+            halo_plane_copy_kernel<<<blocks, 256, 0, d.stream>>>(peer_buf(cc), me.buf[which], axis, n - 2, 0, c.nx, c.ny, c.nz, d.state);
+            h->kernel_launches += 1;
+        }
+        if (coord[axis] + 1 < dims[axis]) {  // high neighbour's plane 1 -> my plane n-1
+            int cc[3] = {coord[0], coord[1], coord[2]};
+            cc[axis] += 1;
+            halo_plane_copy_kernel<<<blocks, 256, 0, d.stream>>>(peer_buf(cc), me.buf[which], axis, 1, n - 1, c.nx, c.ny, c.nz, d.state);
+            h->kernel_launches += 1;
+        }
+        barrier();  // the next axis (or the next step kernel) touches cells this one has read or written
+    }
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
 int cart_update_halo(b2s_diff3d *h, int which)
 {
+    if (h->slabs.size() == 1 && h->multi) return cart_update_halo_multiprocess(h, which);
     const b2s_diff3d_config &c = h->cfg;
     int dims[3];
     cart_dims(c, dims);
@@ -522,8 +572,6 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
         const int dx_ = cfg->dimx > 1 ? cfg->dimx : 1, dy_ = cfg->dimy > 1 ? cfg->dimy : 1;
         B2S_REQUIRE(cfg->dimx >= 0 && cfg->dimy >= 0 && cfg->nslabs_total % (dx_ * dy_) == 0, B2S_ERR_BAD_ARG,
                     "dims (%d, %d, .) do not divide %d ranks", cfg->dimx, cfg->dimy, cfg->nslabs_total);
-        B2S_REQUIRE(dx_ * dy_ == 1 || cfg->slab_count == cfg->nslabs_total, B2S_ERR_NOT_IMPLEMENTED,
-                    "a decomposition in x or y needs an in-process handle (slab_count == nslabs_total)");
     }
     int ndev = 0;
     B2S_CHECK(b2s_device_count(&ndev));
@@ -718,6 +766,7 @@ int b2s_diff3d_set_initial(b2s_diff3d *h, const double *Ht_host)
         B2S_CUDA(cudaMemset(s.buf[1], 0, n * sizeof(double)));                                 // Htau2 = @zeros
         B2S_CUDA(cudaMemset(s.ticket, 0, 64));
         B2S_CUDA(cudaMemset(s.slots, 0, sizeof(RankSlots)));
+        B2S_CUDA(cudaMemset(s.arena + h->ar.off_cart, 0, sizeof(CartSync)));
     }
     h->launched = 0;
     h->seq = 1;
@@ -805,6 +854,7 @@ int b2s_diff3d_ipc_connect(b2s_diff3d *h, const void *all_blobs, int nblobs)
     guard.set(s.dev);
     const IpcBlob *blobs = (const IpcBlob *)all_blobs;
     std::vector<RankSlots *> tbl(nblobs, nullptr);
+    h->peer_base.assign(nblobs, nullptr);
     for (int r = 0; r < nblobs; ++r) {
         B2S_REQUIRE(blobs[r].rank == r && blobs[r].arena_bytes == h->ar.bytes, B2S_ERR_BAD_ARG,
                     "blob %d does not describe slab %d of a compatible handle", r, r);
@@ -818,11 +868,19 @@ int b2s_diff3d_ipc_connect(b2s_diff3d *h, const void *all_blobs, int nblobs)
             base = (char *)m;
         }
         tbl[r] = (RankSlots *)(base + h->ar.off_slots);
-        if (r == s.rank - 1) { s.lo_buf[0] = (double *)(base + h->ar.off_buf[0]); s.lo_buf[1] = (double *)(base + h->ar.off_buf[1]); }
-        if (r == s.rank + 1) { s.hi_buf[0] = (double *)(base + h->ar.off_buf[0]); s.hi_buf[1] = (double *)(base + h->ar.off_buf[1]); }
+        h->peer_base[r] = base;
+        if (!h->cart) {  // z-slabs: the neighbours' buffers receive the fused halo push
+            if (r == s.rank - 1) { s.lo_buf[0] = (double *)(base + h->ar.off_buf[0]); s.lo_buf[1] = (double *)(base + h->ar.off_buf[1]); }
+            if (r == s.rank + 1) { s.hi_buf[0] = (double *)(base + h->ar.off_buf[0]); s.hi_buf[1] = (double *)(base + h->ar.off_buf[1]); }
+        }
     }
     h->nslots_dst = nblobs;
     B2S_CUDA(cudaMemcpy(h->devs[0].peer_table, tbl.data(), sizeof(RankSlots *) * nblobs, cudaMemcpyHostToDevice));
+    if (h->cart) {  // phase mailboxes of all ranks (cart_barrier_kernel)
+        std::vector<CartSync *> ct(nblobs, nullptr);
+        for (int r = 0; r < nblobs; ++r) ct[r] = (CartSync *)(h->peer_base[r] + h->ar.off_cart);
+        B2S_CUDA(cudaMemcpy(s.arena + h->ar.off_cart_table, ct.data(), sizeof(CartSync *) * nblobs, cudaMemcpyHostToDevice));
+    }
     h->connected = true;
     return B2S_OK;
 }

@@ -41,6 +41,12 @@ struct RankSlots {
     unsigned long long seq[2][kMaxRanks];
 };
 
+// General decompositions with one process per GPU: phase mailbox in every rank's arena. phase[r] is the last phase rank r
+// has completed (4*seq + k: k-th barrier of the PT iteration with sequence number seq), written by rank r itself.
+struct CartSync {
+    unsigned long long phase[kMaxRanks];
+};
+
 struct StepParams {
     const double *Ht;
     const double *A;  // Htau  (read)
@@ -305,6 +311,32 @@ __global__ void __launch_bounds__(256) halo_plane_copy_kernel(const double *__re
         else { ps = (size_t)a + (size_t)nx * (b + (size_t)ny * sp); pd = (size_t)a + (size_t)nx * (b + (size_t)ny * dp); }
         dst[pd] = src[ps];
     }
+}
+
+// Barrier between the ranks of a general decomposition hosted by different processes: announces "this rank has finished
+// everything before barrier k of the current PT iteration" in every rank's mailbox and waits until all ranks have done
+// the same. The phase number is derived from the device-resident sequence number, which advances identically on all
+// ranks (the host-side launch counts may differ after convergence). One thread per rank.
+__global__ void cart_barrier_kernel(PTState *state, CartSync *mine, CartSync *const *peers, int nranks, int myrank, int k,
+                                    long long timeout_cycles)
+{
+    if (state->done) return;
+    const int t = threadIdx.x;
+    const unsigned long long phase = 4ull * state->seq + (unsigned long long)k;
+    __shared__ int failed;
+    if (t == 0) failed = 0;
+    __syncthreads();
+    if (t < nranks) {
+        __threadfence_system();  // the plane copies / the step kernel of this rank are visible before the flag
+        st_release_sys_u64(&peers[t]->phase[myrank], phase);
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(&mine->phase[t]) < phase) {
+            if (clock64() - t0 > timeout_cycles) { failed = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (t == 0 && failed) { state->error = 1; state->done = 1; }
 }
 
 // One block: consume the partial sums of all ranks in rank order (deterministic, identical on every GPU).

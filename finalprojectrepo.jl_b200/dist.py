@@ -60,7 +60,8 @@ def connect(handle, dist=None):
 
 
 def gather_global(handle, dist=None):
-    """gather!(Array(Ht), H_g) across processes: rank 0 receives (nx, ny, nz*world), others None."""
+    """gather!(Array(Ht), H_g) across processes: rank 0 receives (nx, ny, nz*world) -- (nx*dimx, ny*dimy, nz*dimz) for a
+    general decomposition --, others None."""
     import numpy as np
     loc = handle.gather()
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
@@ -69,4 +70,9 @@ def gather_global(handle, dist=None):
     dist.gather_object(loc, parts, dst=0)
     if dist.get_rank() != 0:
         return None
+    if handle.dims[0] * handle.dims[1] > 1:  # general decomposition: every rank filled its own block of the global array
+        out = parts[0].copy(order="F")
+        for q in parts[1:]:
+            out += q  # the blocks are disjoint, everything else is zero
+        return out
     return np.asfortranarray(np.concatenate(parts, axis=2))

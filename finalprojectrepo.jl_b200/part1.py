@@ -29,8 +29,8 @@ class Diffusion3D:
     def __init__(self, nx, ny, nz, nslabs=1, devices=None, slab_begin=0, slab_count=None,
                  halo_mode=capi.HALO_REFERENCE_LAG2, bc_mode=capi.BC_LITERAL, scale_physical_size=False,
                  kernel_variant=capi.KERNEL_AUTO, batch=0, dims=None):
-        """dims = (dimx, dimy, dimz): general Cartesian rank grid like init_global_grid's (in-process handles only;
-        ranks in MPI Cartesian order, z fastest). Default: z-slabs (1, 1, nslabs)."""
+        """dims = (dimx, dimy, dimz): general Cartesian rank grid like init_global_grid's (ranks in MPI Cartesian order,
+        z fastest; in-process or one process per GPU). Default: z-slabs (1, 1, nslabs)."""
         self._L = capi.lib()
         self.n = (int(nx), int(ny), int(nz))
         if dims is not None:
@@ -38,6 +38,8 @@ class Diffusion3D:
             nslabs = dims[0] * dims[1] * dims[2]
         self.dims = dims if dims is not None else (1, 1, int(nslabs))
         self.nslabs = int(nslabs)
+        if dims is not None and slab_count is None and devices is None:
+            devices = [0] * self.nslabs
         self.slab_begin = int(slab_begin)
         self.slab_count = self.nslabs if slab_count is None else int(slab_count)
         devices = list(devices) if devices is not None else [0] * self.slab_count

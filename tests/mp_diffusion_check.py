@@ -1,7 +1,7 @@
 """One process per GPU (torchrun): z-slab diffusion with the fused NVLink halo push + peer-store norm exchange, checked
 against the oracle's rank emulation. Every rank verifies its own slab bit-for-bit. Usage (2+ GPUs):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      tests/mp_diffusion_check.py [nx ny nz] [halo_mode]
+      tests/mp_diffusion_check.py [nx ny nz] [halo_mode] [auto|direct|tma] [dimx dimy dimz]
 """
 import os
 import sys
@@ -21,12 +21,14 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 shape = tuple(int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (64, 64, 34)
 halo = int(sys.argv[4]) if len(sys.argv) >= 5 else 0
 variant = {"auto": 0, "direct": 1, "tma": 2}[sys.argv[5]] if len(sys.argv) >= 6 else 0
+dims = tuple(int(a) for a in sys.argv[6:9]) if len(sys.argv) >= 9 else (1, 1, world)  # general decomposition (optional)
+assert dims[0] * dims[1] * dims[2] == world, (dims, world)
 nsl, begin, count = D.slab_layout(rank, world)
 g = part1.Diffusion3D(*shape, nslabs=nsl, devices=[local], slab_begin=begin, slab_count=count, halo_mode=halo,
-                      scale_physical_size=True, kernel_variant=variant)
+                      scale_physical_size=True, kernel_variant=variant, dims=dims if dims[0] * dims[1] > 1 else None)
 g.init_gaussian()
 D.connect(g, dist)
-o = O.Diffusion3D(*shape, dims=(1, 1, world), halo_mode=halo, scale_physical_size=True)
+o = O.Diffusion3D(*shape, dims=dims, halo_mode=halo, scale_physical_size=True)
 assert np.array_equal(g.get("Ht"), o.get("Ht", rank))
 done = 0
 for chunk in (1, 1, 1, 2, 20):

@@ -59,11 +59,25 @@ def test_inprocess_general_decomposition_on_two_devices(b2s, gpu, oracle, halo_m
     g.close()
 
 
-@pytest.mark.parametrize("args", [["64", "64", "34", "0", "tma"], ["32", "32", "18", "1", "direct"]])
+@pytest.mark.parametrize("args", [["64", "64", "34", "0", "tma"], ["32", "32", "18", "1", "direct"],
+                                  ["64", "20", "18", "0", "tma", "x"], ["20", "18", "16", "1", "direct", "y"],
+                                  ["64", "32", "18", "0", "tma", "xy"]])
 def test_one_process_per_gpu_matches_rank_emulation(b2s, gpu, args):
+    """z-slabs, and general decompositions (split in x, in y, 2x2x1 when 4 GPUs are there) with one process per GPU: the
+    plane copies pull from the neighbours' IPC-mapped arenas, phases are separated by the device-side rank barrier."""
     if gpu < 2:
         pytest.skip("needs 2 GPUs")
     n = min(gpu, 4)
+    args = list(args)
+    if len(args) == 6:
+        kind = args.pop()
+        if kind == "xy":
+            if gpu < 4:
+                pytest.skip("needs 4 GPUs")
+            n, dims = 4, ["2", "2", "1"]
+        else:
+            n, dims = 2, (["2", "1", "1"] if kind == "x" else ["1", "2", "1"])
+        args += dims
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29541",
