@@ -121,6 +121,32 @@ WORKER = textwrap.dedent("""
     dist.all_gather_object(vals, (p.dz, p.dtau, p.total_N, p.nz_g))
     assert all(v == vals[0] for v in vals), vals
     assert D.max_over_ranks(10.0 + rank, dist) == 10.0 + world - 1
+    # gather!-equivalent across processes: z-slabs are concatenated, a general decomposition (here dims = (2,1,1): the
+    # ranks split x) is assembled from the blocks every rank placed into its own copy of the global array
+    import numpy as np
+
+    class Fake:
+        def __init__(self, dims):
+            self.dims = dims
+        def gather(self):
+            if self.dims[0] * self.dims[1] == 1:
+                return np.full((3, 2, 4), float(rank + 1), order="F")
+            a = np.zeros((3 * self.dims[0], 2, 4), order="F")
+            a[3 * rank:3 * rank + 3] = rank + 1
+            return a
+    Hz = D.gather_global(Fake((1, 1, world)), dist)
+    Hx = D.gather_global(Fake((world, 1, 1)), dist)
+    if rank == 0:
+        assert Hz.shape == (3, 2, 4 * world) and all((Hz[:, :, 4 * r:4 * r + 4] == r + 1).all() for r in range(world))
+        assert Hx.shape == (3 * world, 2, 4) and all((Hx[3 * r:3 * r + 3] == r + 1).all() for r in range(world))
+    else:
+        assert Hz is None and Hx is None
+    # the same geometry on every rank for a general decomposition, too
+    cfg2 = capi.Diff3DConfig(20, 18, 16, world, rank, 1, None, 0, 0, 1, 0, 0, world, 1)
+    capi.check(capi.lib().b2s_diff3d_params_for(C.byref(cfg2), C.byref(p)))
+    vals = [None] * world
+    dist.all_gather_object(vals, (p.dx, p.dtau, p.total_N, p.nx_g))
+    assert all(v == vals[0] for v in vals) and vals[0][3] == world * 18 + 2, vals
     dist.barrier()
     dist.destroy_process_group()
     os.write(1, ("rank%dok" % rank).encode() + bytes([10]))
