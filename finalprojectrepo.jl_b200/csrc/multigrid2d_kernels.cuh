@@ -96,9 +96,15 @@ __device__ __forceinline__ Coef make_coef(double h, double c, double alpha)
 // The Gauss-Seidel residual is written with "/ h^2" in the reference (multigrid.jl:279-283). When h^2 is a power of two
 // (every grid with h = 1/2^k: all the configured shapes) x / h^2 and x * (1/h^2) are the same correctly rounded value, so
 // the ~20-instruction FP64 division is replaced by one multiplication without changing a bit; any other h divides.
+// The per-level constants sit right behind the call block in device memory (set_call uploads both with one copy): the
+// address does not depend on a loaded pointer, so this load and the one of cp->done are issued together.
+__device__ __forceinline__ const LevelCoef *level_consts(const MGCall *cp, int level)
+{
+    return reinterpret_cast<const LevelCoef *>(cp + 1) + level;
+}
 __device__ __forceinline__ Coef level_coef(const MGCall *cp, int level)
 {
-    const LevelCoef *L = cp->lev + level;
+    const LevelCoef *L = level_consts(cp, level);
     Coef k;
     k.C = L->C; k._h2 = L->_h2; k.w = L->wJ;
     return k;
@@ -504,11 +510,14 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     extern __shared__ __align__(16) double tsm[];
     double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
     const MGCall *cp = a.cp;
-    if (cp->done) return;
+    // Levels below the finest get their array pointers from the launch arguments: their staging loads are issued before
+    // the call block (done flag, constants) has arrived, which takes one L2 round trip off the critical path of these
+    // latency-bound kernels; the loads of a cycle that turns out to be a no-op are harmless reads.
     const double *u = a.u_in, *rhs = a.rhs;
-    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
-    const int apply_bcs = cp->apply_bcs;
-    const Coef k = level_coef(cp, a.level);
+    if (a.level == 0) {
+        if (cp->done) return;
+        u = cp->u; rhs = cp->rhs;
+    }
     const int nx = a.nx, ny = a.ny;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int gx0 = X0 - 3, gy0 = Y0 - 3;
@@ -529,8 +538,12 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
             cp_async8(Fr + c, rhs + p, in && frow && c >= 1 && c < kTW + 5);
         }
     }
+    const int done = a.level == 0 ? 0 : cp->done;
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = level_coef(cp, a.level);
     cp_async_wait_all();
     __syncthreads();
+    if (done) return;
     // block-uniform: does the widest stencil window stay strictly inside the domain?
     const bool inner = X0 - 2 >= 1 && Y0 - 2 >= 1 && X0 + kTW + 1 <= nx - 2 && Y0 + kTH + 1 <= ny - 2;
     if (inner) {
@@ -600,12 +613,12 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     __shared__ double red[32];
     double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows, *Cw = tsm + 3 * kTP * kTRows;
     const MGCall *cp = a.cp;
-    if (cp->done) return;
     const double *rhs = a.rhs;
     double *out = a.u_out;
-    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
-    const int apply_bcs = cp->apply_bcs;
-    const Coef k = level_coef(cp, a.level);
+    if (a.level == 0) {  // finest level: the arrays are the caller's (see mg_down_kernel for the ordering below)
+        if (cp->done) return;
+        rhs = cp->rhs; out = cp->u;
+    }
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const int gx0 = X0 - 3, gy0 = Y0 - 3;
@@ -637,8 +650,12 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
             cp_async8(Cw + r * kCW + c, a.ec + (in ? rowoff + I : 0), in);
         }
     }
+    const int done = a.level == 0 ? 0 : cp->done;
+    const int apply_bcs = cp->apply_bcs;
+    const Coef k = level_coef(cp, a.level);
     cp_async_wait_all();
     __syncthreads();
+    if (done) return;
     // u_f .= u_f - corr_f on tile+2
     for (int idx = threadIdx.x; idx < (kTW + 4) * (kTH + 4); idx += kTileThreads) {
         const int r = idx / (kTW + 4), c = idx - r * (kTW + 4);

@@ -51,7 +51,7 @@ __device__ __forceinline__ RbCoef make_rb_coef(double h, double c)
 
 __device__ __forceinline__ RbCoef level_rb_coef(const MGCall *cp, int level)
 {
-    const LevelCoef *L = cp->lev + level;
+    const LevelCoef *L = level_consts(cp, level);
     RbCoef k;
     k.C = L->C; k.h2 = L->h2; k.w = L->wGS; k.inv_h2 = L->inv_h2;
     return k;
@@ -186,22 +186,27 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_rb_kernel(const TileArgs
     extern __shared__ __align__(16) double tsm[];
     double *UR = tsm, *UB = tsm + kPlane, *FR = tsm + 2 * kPlane, *FB = tsm + 3 * kPlane;
     const MGCall *cp = a.cp;
-    if (cp->done) return;
+    // below the finest level the staging loads are issued before the call block has arrived (see mg_down_kernel)
     const double *u = a.u_in, *rhs = a.rhs;
-    if (a.level == 0) { u = cp->u; rhs = cp->rhs; }
-    const int apply_bcs = cp->apply_bcs;
-    const RbCoef k = level_rb_coef(cp, a.level);
-    const Coef kr = level_coef(cp, a.level);  // C and 1/h^2 of the residual (the weight is not used)
+    if (a.level == 0) {
+        if (cp->done) return;
+        u = cp->u; rhs = cp->rhs;
+    }
     const int nx = a.nx, ny = a.ny;
     const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
     const int gx0 = X0 - HALO, gy0 = Y0 - HALO;
     rb_stage<kW, kRows, kP2>(UR, UB, u, gx0, gy0, nx, ny, 0, kW, 0, kRows);
     rb_stage<kW, kRows, kP2>(FR, FB, rhs, gx0, gy0, nx, ny, 1, kW - 1, 1, kRows - 1);
+    const int done = a.level == 0 ? 0 : cp->done;
+    const int apply_bcs = cp->apply_bcs;
+    const RbCoef k = level_rb_coef(cp, a.level);
+    const Coef kr = level_coef(cp, a.level);  // C and 1/h^2 of the residual (the weight is not used)
     cp_async_wait_all();
     __syncthreads();
+    if (done) return;
     // block-uniform: does the widest window (halo 5) stay strictly inside the domain?
     const bool inner = X0 - 5 >= 1 && Y0 - 5 >= 1 && X0 + TW + 4 <= nx - 2 && Y0 + TH + 4 <= ny - 2;
-    const bool div = !cp->lev[a.level].exact;
+    const bool div = !level_consts(cp, a.level)->exact;
     if (inner && !div) rb_down_sweeps<TW, TH, false, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else if (inner) rb_down_sweeps<TW, TH, false, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else if (!div) rb_down_sweeps<TW, TH, true, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
@@ -272,12 +277,12 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
     __shared__ double red[32];
     double *UR = tsm, *UB = tsm + kPlane, *FR = tsm + 2 * kPlane, *FB = tsm + 3 * kPlane, *Cw = tsm + 4 * kPlane;
     const MGCall *cp = a.cp;
-    if (cp->done) return;
     const double *rhs = a.rhs;
     double *out = a.u_out;
-    if (a.level == 0) { rhs = cp->rhs; out = cp->u; }
-    const int apply_bcs = cp->apply_bcs;
-    const RbCoef k = level_rb_coef(cp, a.level);
+    if (a.level == 0) {
+        if (cp->done) return;
+        rhs = cp->rhs; out = cp->u;
+    }
     const int nx = a.nx, ny = a.ny, nxc = a.nxc, nyc = a.nyc;
     const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
     const int gx0 = X0 - HALO, gy0 = Y0 - HALO;
@@ -294,8 +299,12 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
             cp_async8(Cw + r * kCW + c, a.ec + (in ? rowoff + I : 0), in);
         }
     }
+    const int done = a.level == 0 ? 0 : cp->done;
+    const int apply_bcs = cp->apply_bcs;
+    const RbCoef k = level_rb_coef(cp, a.level);
     cp_async_wait_all();
     __syncthreads();
+    if (done) return;
     // u_f .= u_f - corr_f on tile+4 (multigrid.jl:136-139): one warp per staged row, one column parity per pass (the
     // interpolation formula and the colour plane are then uniform across the warp)
     for (int r = threadIdx.x >> 5; r < kRows; r += kTileThreads / 32) {
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_rb_kernel(const TileArgs a
     }
     __syncthreads();
     const bool inner = X0 - 3 >= 1 && Y0 - 3 >= 1 && X0 + TW + 2 <= nx - 2 && Y0 + TH + 2 <= ny - 2;
-    const bool div = !cp->lev[a.level].exact;
+    const bool div = !level_consts(cp, a.level)->exact;
     double acc;
     if (inner && !div) acc = rb_up_sweeps<TW, TH, false, false>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
     else if (inner) acc = rb_up_sweeps<TW, TH, false, true>(UR, UB, FR, FB, gx0, gy0, nx, ny, k);
