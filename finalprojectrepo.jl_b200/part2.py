@@ -407,12 +407,14 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
             l1, _ = hd.stats()
             times.append(ms_i)
         ms = sorted(times)[len(times) // 2]
-        x.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r, nc = hd.solve(x, b, h, 0.0, 1e-6, 100, False)
-        torch.cuda.synchronize()
-        solve_s = time.perf_counter() - t0
+        solve_s = float("inf")
+        for _ in range(3):  # whole MGsolve (x = 0 -> 1e-6), wall clock, best of 3 (the first one also sizes the batches)
+            x.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r, nc = hd.solve(x, b, h, 0.0, 1e-6, 100, False)
+            torch.cuda.synchronize()
+            solve_s = min(solve_s, time.perf_counter() - t0)
         # end to end through the public entry point with HOST arrays: upload of the right-hand side from pinned memory,
         # MGsolve_2DPoisson (x = 0 initial guess created on the device like the reference's CUDA.zeros), download of x
         b_host = torch.from_numpy(np.ascontiguousarray(np.random.default_rng(seed).random((n, n)).T)).pin_memory()
