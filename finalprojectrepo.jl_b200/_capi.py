@@ -91,6 +91,8 @@ SIGNATURES = {
     "b2s_diff3d_device_ptr": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "b2s_diff3d_upload_state": (_i, [_vp, _i, _vp]),
     "b2s_diff3d_download_state": (_i, [_vp, _i, _vp]),
+    "b2s_diff3d_download_state_async": (_i, [_vp, _i, _vp]),
+    "b2s_diff3d_sync": (_i, [_vp]),
     "b2s_diff3d_stats": (_i, [_vp, _llp, _dp]),
     "b2s_residual2d": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i, _vp]),
     "b2s_iteration2d": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _d, _i, _dp, _vp]),

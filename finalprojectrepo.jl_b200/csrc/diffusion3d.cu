@@ -215,6 +215,9 @@ struct DeviceCtx {  // one per distinct device of the handle: stream, PT state, 
     int err_hist_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_bar = nullptr;  // cross-device ordering of the plane copies (general decompositions)
+    cudaStream_t copy_stream = nullptr;          // b2s_diff3d_download_state_async
+    cudaEvent_t ev_work = nullptr, ev_down = nullptr;
+    bool download_pending = false;
 };
 
 }  // namespace
@@ -451,6 +454,10 @@ int run_loop(b2s_diff3d *h, PTState st, PTState *out)
     B2S_CHECK(upload_state(h, st));
     for (DeviceCtx &d : h->devs) {
         B2S_CUDA(cudaSetDevice(d.dev));
+        if (d.download_pending) {  // a pipelined download still reads the current buffer: iterations overwrite it
+            B2S_CUDA(cudaStreamWaitEvent(d.stream, d.ev_down, 0));
+            d.download_pending = false;
+        }
         B2S_CUDA(cudaEventRecord(d.ev0, d.stream));
     }
     int batch = h->cfg.batch > 0 ? h->cfg.batch : 0;
@@ -538,6 +545,9 @@ int destroy_impl(b2s_diff3d *h)
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_bar) cudaEventDestroy(d.ev_bar);
+        if (d.copy_stream) { cudaStreamSynchronize(d.copy_stream); cudaStreamDestroy(d.copy_stream); }
+        if (d.ev_work) cudaEventDestroy(d.ev_work);
+        if (d.ev_down) cudaEventDestroy(d.ev_down);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     for (Slab &s : h->slabs) {
@@ -1038,7 +1048,47 @@ int b2s_diff3d_upload_state(b2s_diff3d *h, int slab, const double *Ht_host)
     const int cur = (int)(h->launched & 1);
     const size_t bytes = h->ar.cells * sizeof(double);
     B2S_CUDA(cudaMemcpyAsync(s.Ht, Ht_host, bytes, cudaMemcpyHostToDevice, d.stream));
+    if (d.download_pending) {  // a pipelined download may still be reading the buffer that is overwritten next
+        B2S_CUDA(cudaStreamWaitEvent(d.stream, d.ev_down, 0));
+        d.download_pending = false;
+    }
     B2S_CUDA(cudaMemcpyAsync(s.buf[cur], s.Ht, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    return B2S_OK;
+}
+
+int b2s_diff3d_download_state_async(b2s_diff3d *h, int slab, double *Htau_host)
+{
+    B2S_REQUIRE(h && Htau_host, B2S_ERR_BAD_ARG, "NULL argument");
+    const int i = slab_index(h, slab);
+    B2S_REQUIRE(i >= 0, B2S_ERR_BAD_ARG, "slab %d is not hosted by this handle", slab);
+    Slab &s = h->slabs[i];
+    DeviceCtx &d = h->devs[s.devslot];
+    DeviceGuard guard;
+    guard.set(s.dev);
+    if (!d.copy_stream) {
+        B2S_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+        B2S_CUDA(cudaEventCreateWithFlags(&d.ev_work, cudaEventDisableTiming));
+        B2S_CUDA(cudaEventCreateWithFlags(&d.ev_down, cudaEventDisableTiming));
+    }
+    const int cur = (int)(h->launched & 1);
+    B2S_CUDA(cudaEventRecord(d.ev_work, d.stream));
+    B2S_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev_work, 0));
+    B2S_CUDA(cudaMemcpyAsync(Htau_host, s.buf[cur], h->ar.cells * sizeof(double), cudaMemcpyDeviceToHost, d.copy_stream));
+    B2S_CUDA(cudaEventRecord(d.ev_down, d.copy_stream));
+    d.download_pending = true;
+    return B2S_OK;
+}
+
+int b2s_diff3d_sync(b2s_diff3d *h)
+{
+    B2S_REQUIRE(h, B2S_ERR_BAD_ARG, "NULL handle");
+    DeviceGuard guard;
+    guard.set(h->devs[0].dev);
+    for (DeviceCtx &d : h->devs) {
+        B2S_CUDA(cudaSetDevice(d.dev));
+        B2S_CUDA(cudaStreamSynchronize(d.stream));
+        if (d.copy_stream) B2S_CUDA(cudaStreamSynchronize(d.copy_stream));
+    }
     return B2S_OK;
 }
 

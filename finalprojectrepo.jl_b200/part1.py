@@ -140,6 +140,14 @@ class Diffusion3D:
         slab = self.slab_begin if slab is None else slab
         capi.check(self._L.b2s_diff3d_download_state(self._h, slab, capi.ptr(out_host)))
 
+    def download_state_async(self, out_host, slab=None):
+        """Pipelined download (separate copy stream): overlaps with the next upload_state; valid after sync()."""
+        slab = self.slab_begin if slab is None else slab
+        capi.check(self._L.b2s_diff3d_download_state_async(self._h, slab, capi.ptr(out_host)))
+
+    def sync(self):
+        capi.check(self._L.b2s_diff3d_sync(self._h))
+
     def stats(self):
         n, ms = C.c_longlong(), C.c_double()
         capi.check(self._L.b2s_diff3d_stats(self._h, C.byref(n), C.byref(ms)))

@@ -154,6 +154,11 @@ int b2s_diff3d_device_ptr(b2s_diff3d *h, int slab, int which, double **dev_out);
  * uploads Ht and Htau (Htau := Ht) from host memory / downloads Htau. */
 int b2s_diff3d_upload_state(b2s_diff3d *h, int slab, const double *Ht_host);
 int b2s_diff3d_download_state(b2s_diff3d *h, int slab, double *Htau_host);
+/* Pipelined variant for back-to-back jobs: the download runs on a separate copy stream after the work enqueued so far,
+ * so that the NEXT b2s_diff3d_upload_state (host -> Ht) overlaps with it on the other DMA direction; the upload's final
+ * Ht -> Htau copy and everything after it wait for the download. Htau_host (pinned) is valid after b2s_diff3d_sync(). */
+int b2s_diff3d_download_state_async(b2s_diff3d *h, int slab, double *Htau_host);
+int b2s_diff3d_sync(b2s_diff3d *h);
 /* Bookkeeping for gpu_launches / timing: kernels launched so far; device time (ms, CUDA events on the
  * launching stream) of the last solve_timestep / iterate call, max over hosted slabs. */
 int b2s_diff3d_stats(const b2s_diff3d *h, long long *kernel_launches, double *last_call_ms);

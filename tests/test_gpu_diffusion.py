@@ -309,6 +309,10 @@ def test_c_level_run_set_initial_state_io_and_device_ptrs(b2s, gpu, oracle):
     host = torch.empty(n[0] * n[1] * n[2], dtype=torch.float64).pin_memory()
     g.download_state(host)
     assert np.array_equal(host.numpy().reshape(n, order="F"), o.get("Htau"))
+    host2 = torch.zeros(n[0] * n[1] * n[2], dtype=torch.float64).pin_memory()
+    g.download_state_async(host2)  # pipelined variant: valid after sync()
+    g.sync()
+    assert torch.equal(host2, host)
     g.upload_state(host)  # Ht := Htau := host
     assert np.array_equal(g.get("Ht"), o.get("Htau")) and np.array_equal(g.get("Htau"), o.get("Htau"))
     # L0 kernel on the handle's device arrays: one more iteration by hand equals iterate(1)
