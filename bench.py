@@ -342,13 +342,20 @@ def _e2e(args, s, n, N, cells, iters, torch, sync_all, max_over_ranks, nbytes):
         s.upload_state(host_in); s.iterate(iters, want_hist=False); s.download_state(host_out)
     sync_all()
     # Every step: host -> device copy of its input state (pinned), `iters` PT iterations, device -> host copy of its result
-    # (pinned). Consecutive steps are independent jobs, so the download of step k runs on the copy stream while step
-    # k+1's upload uses the other DMA direction (b2s_diff3d_download_state_async); nothing is skipped or cached.
+    # (pinned). Consecutive steps are independent jobs, so they are double-buffered like a serving pipeline: the upload of
+    # step k+1 goes to a staging array on the copy stream while step k iterates, and the download of step k overlaps with
+    # step k+1 (b2s_diff3d_upload_state_async / _commit_upload / _download_state_async). Nothing is skipped or cached:
+    # every step's 1 GiB goes in and its 1 GiB result comes out inside the timed region.
     outs = [host_out, torch.empty(n * n * n, dtype=torch.float64).pin_memory()]
     t0 = time.perf_counter()
+    e2e_dev_ms = 0.0
+    s.upload_state_async(host_in)
     for k in range(args.steps):
-        s.upload_state(host_in)
+        s.commit_upload()
+        if k + 1 < args.steps:
+            s.upload_state_async(host_in)
         s.iterate(iters, want_hist=False)
+        e2e_dev_ms += s.stats()[1]
         s.download_state_async(outs[k & 1])
     s.sync()
     sync_all()
@@ -356,7 +363,8 @@ def _e2e(args, s, n, N, cells, iters, torch, sync_all, max_over_ranks, nbytes):
     host_out = outs[(args.steps - 1) & 1]
     e2e = {"value": BYTES_PER_CELL * cells * iters * args.steps * N / e2e_wall / 1e9, "unit": "GB/s",
            "h2d_bytes_per_step": nbytes * N, "d2h_bytes_per_step": nbytes * N,
-           "ms_per_step": e2e_wall / args.steps * 1e3, "checksum": float(host_out[:: 4097].sum())}
+           "ms_per_step": e2e_wall / args.steps * 1e3, "iterations_device_ms_per_step": e2e_dev_ms / args.steps,
+           "checksum": float(host_out[:: 4097].sum())}
     s.close()
     return e2e
 

@@ -92,6 +92,8 @@ SIGNATURES = {
     "b2s_diff3d_upload_state": (_i, [_vp, _i, _vp]),
     "b2s_diff3d_download_state": (_i, [_vp, _i, _vp]),
     "b2s_diff3d_download_state_async": (_i, [_vp, _i, _vp]),
+    "b2s_diff3d_upload_state_async": (_i, [_vp, _i, _vp]),
+    "b2s_diff3d_commit_upload": (_i, [_vp, _i]),
     "b2s_diff3d_sync": (_i, [_vp]),
     "b2s_diff3d_stats": (_i, [_vp, _llp, _dp]),
     "b2s_residual2d": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i, _vp]),

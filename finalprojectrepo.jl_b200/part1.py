@@ -145,6 +145,16 @@ class Diffusion3D:
         slab = self.slab_begin if slab is None else slab
         capi.check(self._L.b2s_diff3d_download_state_async(self._h, slab, capi.ptr(out_host)))
 
+    def upload_state_async(self, Ht_host, slab=None):
+        """Stage the NEXT job's state on the copy stream (overlaps with running iterations); commit_upload() makes it
+        the current state."""
+        slab = self.slab_begin if slab is None else slab
+        capi.check(self._L.b2s_diff3d_upload_state_async(self._h, slab, capi.ptr(Ht_host)))
+
+    def commit_upload(self, slab=None):
+        slab = self.slab_begin if slab is None else slab
+        capi.check(self._L.b2s_diff3d_commit_upload(self._h, slab))
+
     def sync(self):
         capi.check(self._L.b2s_diff3d_sync(self._h))
 

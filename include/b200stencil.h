@@ -154,10 +154,15 @@ int b2s_diff3d_device_ptr(b2s_diff3d *h, int slab, int which, double **dev_out);
  * uploads Ht and Htau (Htau := Ht) from host memory / downloads Htau. */
 int b2s_diff3d_upload_state(b2s_diff3d *h, int slab, const double *Ht_host);
 int b2s_diff3d_download_state(b2s_diff3d *h, int slab, double *Htau_host);
-/* Pipelined variant for back-to-back jobs: the download runs on a separate copy stream after the work enqueued so far,
- * so that the NEXT b2s_diff3d_upload_state (host -> Ht) overlaps with it on the other DMA direction; the upload's final
- * Ht -> Htau copy and everything after it wait for the download. Htau_host (pinned) is valid after b2s_diff3d_sync(). */
+/* Pipelined variant for back-to-back jobs: the result is copied aside on the device (an extra nx*ny*nz array, allocated
+ * on first use) and transferred from there on a separate copy stream, so the handle is free for the next job at once.
+ * Htau_host (pinned) is valid after b2s_diff3d_sync(). */
 int b2s_diff3d_download_state_async(b2s_diff3d *h, int slab, double *Htau_host);
+/* Double-buffered upload for back-to-back jobs: _async copies the NEXT job's state into a staging array on the copy
+ * stream (it overlaps with the iterations of the current job; the staging array, nx*ny*nz doubles, is allocated on
+ * first use); _commit makes it the current state (Ht := Htau := staged) on the compute stream once it has arrived. */
+int b2s_diff3d_upload_state_async(b2s_diff3d *h, int slab, const double *Ht_host);
+int b2s_diff3d_commit_upload(b2s_diff3d *h, int slab);
 int b2s_diff3d_sync(b2s_diff3d *h);
 /* Bookkeeping for gpu_launches / timing: kernels launched so far; device time (ms, CUDA events on the
  * launching stream) of the last solve_timestep / iterate call, max over hosted slabs. */

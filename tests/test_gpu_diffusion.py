@@ -313,6 +313,10 @@ def test_c_level_run_set_initial_state_io_and_device_ptrs(b2s, gpu, oracle):
     g.download_state_async(host2)  # pipelined variant: valid after sync()
     g.sync()
     assert torch.equal(host2, host)
+    g.iterate(3)
+    g.upload_state_async(host)  # double-buffered upload: staged on the copy stream, then committed
+    g.commit_upload()
+    assert np.array_equal(g.get("Ht"), o.get("Htau")) and np.array_equal(g.get("Htau"), o.get("Htau"))
     g.upload_state(host)  # Ht := Htau := host
     assert np.array_equal(g.get("Ht"), o.get("Htau")) and np.array_equal(g.get("Htau"), o.get("Htau"))
     # L0 kernel on the handle's device arrays: one more iteration by hand equals iterate(1)
