@@ -2201,7 +2201,9 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
     }
     const double *rhs_g = a.rhs_in != nullptr ? a.rhs_in : cp->rhs;
     double *u_g = a.u_io != nullptr ? a.u_io : cp->u;
+    __shared__ LevelCoef slev[kMaxLevels];  // per-level constants of this call (host-computed), fetched once up front
     {
+        if (threadIdx.x < a.nlev) slev[threadIdx.x] = *level_consts(cp, a.level0 + threadIdx.x);
         const int n = a.nx[0] * a.ny[0];
         for (int p = threadIdx.x; p < n; p += blockDim.x) {
             F[0][p] = rhs_g[p];
@@ -2209,14 +2211,19 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
         }
         __syncthreads();
     }
+    auto coef_of = [&](int l) {
+        Coef k;
+        k.C = slev[l].C; k._h2 = slev[l]._h2; k.w = slev[l].wJ;
+        return k;
+    };
     double last_ss = 0.0;
     if (a.prof != nullptr && threadIdx.x == 0) a.prof[0] = 0;
     coarse_stamp(a);
     // ---- downward leg ---------------------------------------------------------------------------------------
     for (int l = 0; l + 1 < a.nlev; ++l) {
         const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
-        const double h = level_h(cp, a.level0 + l);
-        const Coef k = make_coef(h, c, 4.0 / 5.0);
+        const double h = slev[l].h;
+        const Coef k = coef_of(l);
         if (a.smoother == B2S_SMOOTH_RBGS) {
             sm_rbgs(bg, U[l], F[l], nx, ny, h, c, false);
             sm_rbgs(bg, U[l], F[l], nx, ny, h, c, false);
@@ -2224,7 +2231,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
             sm_jacobi(bg, U[l], F[l], T[l], nx, ny, k, false);
             sm_jacobi(bg, T[l], F[l], U[l], nx, ny, k, false);
         }
-        const Coef kr = make_coef(h, c, 1.0);
+        const Coef kr = k;  // the residual uses C and 1/h^2 only
         for (Idx2 q(threadIdx.x, blockDim.x, nxc); q.p < nxc * nyc; q.next()) {
             const int p = q.p, J = q.j;
             int I = q.i;
@@ -2242,7 +2249,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
     {
         const int l = a.nlev - 1;
         const int nx = a.nx[l], ny = a.ny[l];
-        const double h = level_h(cp, a.level0 + l);
+        const double h = slev[l].h;
         if (nx * ny <= 1024) {
             if (threadIdx.x < 32) {
                 WarpGroup wg;
@@ -2257,8 +2264,8 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
     // ---- upward leg -------------------------------------------------------------------------------------------
     for (int l = a.nlev - 2; l >= 0; --l) {
         const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
-        const double h = level_h(cp, a.level0 + l);
-        const Coef k = make_coef(h, c, 4.0 / 5.0);
+        const double h = slev[l].h;
+        const Coef k = coef_of(l);
         for (Idx2 q(threadIdx.x, blockDim.x, nx); q.p < nx * ny; q.next())
             U[l][q.p] = U[l][q.p] - prolong_value_bc(U[l + 1], nxc, nyc, nx, q.i, q.j, apply_bcs);
         __syncthreads();
