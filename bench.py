@@ -188,6 +188,7 @@ def mg_bench(device, peak):
         from b200stencil import part2
     except Exception as e:  # pragma: no cover
         return {"unavailable": f"{type(e).__name__}: {e}"}
+    time.sleep(3.0)  # the 1 kW diffusion loop has just ended: let clocks and power management settle (latency-bound kernels next)
     try:
         out = part2.bench_vcycle(device=device, hbm_peak_gbs=peak)
     except Exception as e:

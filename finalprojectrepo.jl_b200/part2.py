@@ -397,7 +397,7 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
         hd = MGHandle(n, n, opt if opt is not None else MGOpt(), device)
         x = zeros(n, n, device)
         hd.cycles(x, b, h, 0.0, 1e-6, 3)  # warm-up (graph instantiation)
-        hd.cycles(x, b, h, 0.0, 1e-6, 100)  # ... and let the clocks settle (the cycle is latency-bound: ~10 ms of work)
+        hd.cycles(x, b, h, 0.0, 1e-6, 300)  # ... and let the clocks settle (the cycle is latency-bound: ~30 ms of work)
         times = []
         for _ in range(5):  # median of 5 timings of `ncycles` V-cycles each (CUDA events inside the library)
             x.zero_()
