@@ -86,7 +86,8 @@ function diffusion_3D_kernel_programming(; nx, ny, nz, ttot=1.0, tol=1e-8, use_s
             iter_outer += 1
             check(ccall((:b2s_diff3d_advance_time, lib), Cint, (Ptr{Cvoid},), h[]))   # Ht .= Hτ
         end
-        H_g = zeros(nx, ny, nz * N)
+        dimz = N ÷ (dimx * dimy)
+        H_g = zeros(nx * dimx, ny * dimy, nz * dimz)                                        # zeros(nx*dims[1], …) :144
         check(ccall((:b2s_diff3d_gather, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), h[], H_g))   # also synchronises
         Δt = time() - tic
         cells = (nx - 2) * (ny - 2) * (nz - 2)
