@@ -388,6 +388,10 @@ def _finish(args, rank, N, n, dev, peak, value, ms_per_step, wall, roofline, e2e
                           "kernel_variant": args.variant, "timing": "CUDA events inside the library on its stream, "
                           "max over ranks; wall-clock cross-check in wall_ms_per_step"},
                "wall_ms_per_step": wall / args.steps * 1e3,
+               # the reference's own accounting of the same run (part1_kernel_programming.jl:208-217), for continuity with its
+               # CSVs: 25 + 2 flop per interior cell and iteration; "Throughput" = (6 + 1) doubles per cell and iteration
+               "reference_accounting": {"performance_gflops": value / BYTES_PER_CELL * 27.0,
+                                        "throughput_gbs_7_doubles_per_cell": value / BYTES_PER_CELL * 56.0},
                "roofline": roofline, "e2e": e2e, "gpu_launches": int(nlaunch), "clocks": clocks}
         if cpu is not None:
             out["cpu_baseline"] = cpu
