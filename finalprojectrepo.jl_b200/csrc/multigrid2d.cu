@@ -368,7 +368,11 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
         a.smoother = c.smoother; a.restriction = c.restriction;
         a.sumsq_out = fs == 0 ? h->sumsq_dev : nullptr;
         a.prof = h->prof_dev;
-        mg_coarse_kernel<<<1, 1024, h->coarse_smem, st>>>(a);
+        // one thread per point of the largest resident level (block-wide barriers get cheaper with fewer warps)
+        int cthreads = 64;
+        for (int l = fs; l < h->nlev; ++l) cthreads = std::max(cthreads, h->nx[l] * h->ny[l]);
+        cthreads = std::min(1024, (cthreads + 31) & ~31);
+        mg_coarse_kernel<<<1, cthreads, h->coarse_smem, st>>>(a);
         ++n;
     }
     // upward leg
