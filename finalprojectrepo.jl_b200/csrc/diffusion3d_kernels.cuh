@@ -96,6 +96,16 @@ __device__ __forceinline__ double cell_residual(double c, double xl, double xr, 
            ((p.mD_dz * (zn - c)) - (p.mD_dz * (c - zp))) * p._dz + (c - ht) * p._dt;
 }
 
+// The same residual from ready-made fluxes q(i) = -D_d*(H[i] - H[i-1]) (the macros of part1_kernel_programming.jl:12-20):
+// R = (qx(i+1) - qx(i))*_dx + (qy(j+1) - qy(j))*_dy + (qz(k+1) - qz(k))*_dz + (H - Ht)*_dt. A flux between two cells is the
+// same number for both of them, so the z-marching kernel computes every z flux once (carried to the next plane in a
+// register) and the x flux between the two cells of a thread once: 3 of 28 FP64 operations per cell less, same bits.
+__device__ __forceinline__ double cell_residual_flux(double qx_lo, double qx_hi, double qy_lo, double qy_hi, double qz_lo, double qz_hi,
+                                                     double c, double ht, const StepParams &p)
+{
+    return (qx_hi - qx_lo) * p._dx + (qy_hi - qy_lo) * p._dy + (qz_hi - qz_lo) * p._dz + (c - ht) * p._dt;
+}
+
 // Shared tail of both kernel variants: block partial -> deterministic grid sum -> (optionally) exit test / publish.
 __device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, double *red)
 {
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__((TX / 2) * TY)
     if (tid == 0 && S < nplanes) issue(S);
     mbar_wait(&full[1 % S], (uint32_t)((1 / S) & 1));
     double2 acur = *reinterpret_cast<const double2 *>(sA + (size_t)(1 % S) * C::A_STRIDE + ci);
+    double qz_lo0 = p.mD_dz * (acur.x - aprev.x), qz_lo1 = p.mD_dz * (acur.y - aprev.y);
 
     for (int q = 2; q < nplanes; ++q) {
         const int z = zs + q - 2;
@@ -255,8 +266,13 @@ __global__ void __launch_bounds__((TX / 2) * TY)
         const double2 ynv = *reinterpret_cast<const double2 *>(pc + C::BW);
         const double2 ht = *reinterpret_cast<const double2 *>(sH + (size_t)stc * C::H_STRIDE + hi);
 
-        const double r0 = cell_residual(acur.x, xl, acur.y, ysv.x, ynv.x, aprev.x, anext.x, ht.x, p);
-        const double r1 = cell_residual(acur.y, acur.x, xr, ysv.y, ynv.y, aprev.y, anext.y, ht.y, p);
+        const double qx_mid = p.mD_dx * (acur.y - acur.x);  // between the two cells of this thread
+        const double qz_hi0 = p.mD_dz * (anext.x - acur.x), qz_hi1 = p.mD_dz * (anext.y - acur.y);
+        const double r0 = cell_residual_flux(p.mD_dx * (acur.x - xl), qx_mid, p.mD_dy * (acur.x - ysv.x), p.mD_dy * (ynv.x - acur.x),
+                                             qz_lo0, qz_hi0, acur.x, ht.x, p);
+        const double r1 = cell_residual_flux(qx_mid, p.mD_dx * (xr - acur.y), p.mD_dy * (acur.y - ysv.y), p.mD_dy * (ynv.y - acur.y),
+                                             qz_lo1, qz_hi1, acur.y, ht.y, p);
+        qz_lo0 = qz_hi0; qz_lo1 = qz_hi1;
         const double b0 = acur.x - p.dtau * r0;
         const double b1 = acur.y - p.dtau * r1;
         const size_t g = pxy + sz * z;
