@@ -22,6 +22,32 @@ def test_library_exports_every_declared_symbol(b2s):
     assert capi.lib().b2s_version() == 100
 
 
+def test_header_is_plain_c_and_matches_the_ctypes_mirror(b2s, tmp_path):
+    """include/b200stencil.h must compile as C (what cgo / ccall / ctypes bind against) and its structs must have the
+    layout the Python mirror assumes (sizes and the offsets of the fields appended last)."""
+    import ctypes as C
+    import subprocess
+    from b200stencil import capi
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "b200stencil.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b2s_diff3d_config), offsetof(b2s_diff3d_config, dimx),
+         offsetof(b2s_diff3d_config, dimy), sizeof(b2s_diff3d_params), sizeof(b2s_mg_config), offsetof(b2s_mg_config, fuse_sweeps),
+         sizeof(b2s_ns2d_params), sizeof(b2s_ns2d_stepinfo));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(capi.Diff3DConfig), capi.Diff3DConfig.dimx.offset, capi.Diff3DConfig.dimy.offset, C.sizeof(capi.Diff3DParams),
+            C.sizeof(capi.MGConfig), capi.MGConfig.fuse_sweeps.offset, C.sizeof(capi.NS2DParams), C.sizeof(capi.NS2DStepInfo)]
+    assert got == want, (got, want)
+
+
 def test_no_cpu_fallback(b2s):
     from b200stencil import capi, part1
     if capi.device_count() > 0:
