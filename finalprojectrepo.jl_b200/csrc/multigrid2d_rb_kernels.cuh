@@ -20,6 +20,11 @@
 // Vcycle_2DPoisson! (:121-143). Every point value is produced by exactly the arithmetic of the unfused kernels
 // (mg_rbgs_kernel, mg_restrict_kernel, mg_prolong_kernel); halo points are recomputed redundantly by neighbouring
 // blocks (the halo shrinks by one per half sweep), so results are bit-identical to the unfused path and to the oracle.
+//
+// Tile shapes: 52x32 / 52x16 (staged width 64) and 20x16 / 20x8 (staged width 32): one window row holds at most 32 points
+// of a colour, so a half sweep is done row-wise by lane groups (no per-point index arithmetic); wider tiles fall back to
+// a flat loop. The per-level constants (C, h^2, its exact reciprocal when h^2 is a power of two, the Gauss-Seidel weight)
+// are computed on the host and read from the call block (LevelCoef).
 #pragma once
 #include "multigrid2d_kernels.cuh"
 
@@ -39,16 +44,6 @@ struct RbCfg {
 struct RbCoef {
     double C, h2, w, inv_h2;  // inv_h2: exact reciprocal when h^2 is a power of two (DivH2), unused otherwise
 };
-__device__ __forceinline__ RbCoef make_rb_coef(double h, double c)
-{
-    RbCoef k;
-    k.C = 4.0 + c * (h * h);
-    k.h2 = h * h;
-    k.w = 1.0 * ((h * h) / (4.0 + c * (h * h)));
-    k.inv_h2 = make_div_h2(k.h2).inv;
-    return k;
-}
-
 __device__ __forceinline__ RbCoef level_rb_coef(const MGCall *cp, int level)
 {
     const LevelCoef *L = level_consts(cp, level);
