@@ -16,6 +16,7 @@ OK, ERR_BAD_SIZE, ERR_BAD_ARG, ERR_CUDA, ERR_NOT_IMPLEMENTED, ERR_NO_DEVICE, ERR
 HALO_REFERENCE_LAG2, HALO_CONSISTENT = 0, 1
 BC_LITERAL, BC_PROPER = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+ARITH_KERNEL, ARITH_ARRAY = 0, 1
 COARSE_JACOBI, COARSE_CG = 0, 1
 SMOOTH_JACOBI, SMOOTH_RBGS = 0, 1
 RESTRICT_INJECT, RESTRICT_FW = 0, 1
@@ -36,7 +37,7 @@ class Diff3DConfig(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nslabs_total", C.c_int), ("slab_begin", C.c_int),
                 ("slab_count", C.c_int), ("devices", _ip), ("halo_mode", C.c_int), ("bc_mode", C.c_int),
                 ("scale_physical_size", C.c_int), ("kernel_variant", C.c_int), ("batch", C.c_int),
-                ("dimx", C.c_int), ("dimy", C.c_int)]
+                ("dimx", C.c_int), ("dimy", C.c_int), ("arithmetic", C.c_int)]
 
 
 class Diff3DParams(C.Structure):
@@ -81,7 +82,6 @@ SIGNATURES = {
     "b2s_diff3d_ipc_blob_bytes": (_sz, []),
     "b2s_diff3d_ipc_export": (_i, [_vp, _vp]),
     "b2s_diff3d_ipc_connect": (_i, [_vp, _vp, _i]),
-    "b2s_diff3d_exchange_initial_halo": (_i, [_vp, _i]),
     "b2s_diff3d_solve_timestep": (_i, [_vp, _d, _i, _ip, _dp]),
     "b2s_diff3d_iterate": (_i, [_vp, _i, _vp]),
     "b2s_diff3d_advance_time": (_i, [_vp]),

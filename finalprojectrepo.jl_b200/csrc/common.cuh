@@ -123,6 +123,33 @@ __device__ __forceinline__ bool grid_sum_last_block(double block_partial_thread0
     return tid == 0;
 }
 
+// Same reduction, but the return value (is this the last block?) is valid in EVERY thread of the block, so the whole last
+// block can take part in what follows; *total is written by thread 0 only.
+__device__ __forceinline__ bool grid_sum_last_block_all(double block_partial_thread0, double *partials, unsigned int *ticket,
+                                                        int nblocks, int block_linear, double *sm, double *total)
+{
+    __shared__ bool is_last_all;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    if (tid == 0) {
+        partials[block_linear] = block_partial_thread0;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last_all = (t == (unsigned int)(nblocks - 1));
+    }
+    __syncthreads();
+    if (!is_last_all) return false;
+    __threadfence();
+    double a = 0.0;
+    for (int i = tid; i < nblocks; i += nthreads) a += __ldcg(partials + i);
+    double t = block_sum(a, sm);
+    if (tid == 0) {
+        *total = t;
+        *ticket = 0u;  // ready for the next launch
+    }
+    return true;
+}
+
 // ---- mbarrier + TMA (cp.async.bulk.tensor) -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -137,6 +164,12 @@ __device__ __forceinline__ void fence_mbar_init()
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// generic-proxy accesses (e.g. an acquire of a flag another GPU has released) before later async-proxy (TMA) accesses,
+// all state spaces
+__device__ __forceinline__ void fence_proxy_async_all()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {

@@ -80,11 +80,12 @@ static int grid_blocks_tma(int choice, int nx, int ny, int nz, int zchunk)
     return ((nx + c.tx - 1) / c.tx) * ((ny + c.ty - 1) / c.ty) * ((nz - 2 + zchunk - 1) / zchunk);
 }
 
-static int launch_direct(const StepParams &p, cudaStream_t st)
+static int launch_direct(const StepParams &p, cudaStream_t st, const ArrayArith &aa = ArrayArith())
 {
     dim3 block(kDirBX, kDirBY, 1);
     dim3 grid((p.nx + kDirBX - 1) / kDirBX, (p.ny + kDirBY - 1) / kDirBY, (p.nz - 2 + p.zchunk - 1) / p.zchunk);
-    step_direct_kernel<<<grid, block, 0, st>>>(p);
+    if (p.array_arith) step_direct_kernel<true><<<grid, block, 0, st>>>(p, aa);
+    else step_direct_kernel<false><<<grid, block, 0, st>>>(p, aa);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }
@@ -95,8 +96,10 @@ static bool tma_eligible(int nx, int ny, int nz, const void *a, const void *b, c
 }
 
 // z-chunk: enough blocks for several waves over 148 SMs while keeping the two extra planes per chunk cheap.
+// Returns 0 when even one chunk per xy tile exceeds max_blocks (the block partials would not fit).
 static int pick_zchunk(int nxy_tiles, int nz, int max_blocks)
 {
+    if (nxy_tiles > max_blocks) return 0;
     int zc = env_int("B2S_ZCHUNK", 0);
     const int interior = nz - 2;
     if (zc <= 0) {
@@ -107,7 +110,7 @@ static int pick_zchunk(int nxy_tiles, int nz, int max_blocks)
         zc = (interior + chunks - 1) / chunks;
     }
     zc = std::max(1, std::min(zc, interior));
-    while ((long long)nxy_tiles * ((interior + zc - 1) / zc) > max_blocks) ++zc;
+    while (zc < interior && (long long)nxy_tiles * ((interior + zc - 1) / zc) > max_blocks) ++zc;
     return zc;
 }
 
@@ -153,6 +156,7 @@ extern "C" int b2s_diffusion3d_step_tau(const double *Ht, const double *Htau, do
         const int ch = tma_choice_index((size_t)nx * ny * nz);
         const TmaChoice &c = kTmaChoices[ch];
         p.zchunk = pick_zchunk(((nx + c.tx - 1) / c.tx) * ((ny + c.ty - 1) / c.ty), nz, kMaxPartials);
+        B2S_REQUIRE(p.zchunk > 0, B2S_ERR_BAD_SIZE, "grid %dx%dx%d has more xy tiles than the %d block partials", nx, ny, nz, kMaxPartials);
         CUtensorMap mA, mH;
         B2S_CHECK(make_maps(ch, Htau, Ht, nx, ny, nz, &mA, &mH));
         return launch_tma(ch, mA, mH, p, st);
@@ -160,6 +164,7 @@ extern "C" int b2s_diffusion3d_step_tau(const double *Ht, const double *Htau, do
     B2S_REQUIRE(kernel_variant == B2S_KERNEL_AUTO || kernel_variant == B2S_KERNEL_DIRECT, B2S_ERR_BAD_ARG,
                 "unknown kernel variant %d", kernel_variant);
     p.zchunk = pick_zchunk(((nx + kDirBX - 1) / kDirBX) * ((ny + kDirBY - 1) / kDirBY), nz, kMaxPartials);
+    B2S_REQUIRE(p.zchunk > 0, B2S_ERR_BAD_SIZE, "grid %dx%dx%d has more xy tiles than the %d block partials", nx, ny, nz, kMaxPartials);
     return launch_direct(p, st);
 }
 
@@ -171,10 +176,12 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Arena {  // layout of the per-slab device allocation (identical on every rank -> usable through IPC)
-    size_t cells, off_ht, off_buf[2], off_slots, off_state, off_partials, off_ticket, off_peer_table, off_cart, off_cart_table, bytes;
-    void layout(size_t ncells)
+    size_t cells, off_ht, off_buf[2], off_slots, off_state, off_partials, off_ticket, off_peer_table, off_cart, off_cart_table,
+        off_flags, flag_tiles, bytes;
+    void layout(size_t ncells, size_t max_tiles)
     {
         cells = ncells;
+        flag_tiles = max_tiles;
         size_t o = 0;
         const size_t fb = align_up(ncells * sizeof(double), 1024);
         off_buf[0] = o; o += fb;
@@ -187,6 +194,7 @@ struct Arena {  // layout of the per-slab device allocation (identical on every 
         off_peer_table = o; o += align_up(sizeof(void *) * kMaxRanks, 1024);
         off_cart = o; o += align_up(sizeof(CartSync), 1024);
         off_cart_table = o; o += align_up(sizeof(void *) * kMaxRanks, 1024);
+        off_flags = o; o += align_up(4 * max_tiles * sizeof(unsigned long long), 1024);  // halo flags [4][max_tiles]
         bytes = o;
     }
 };
@@ -203,6 +211,10 @@ struct Slab {
     CUtensorMap mapHt, mapBuf[2];
     // neighbours' buffers (local pointer, peer pointer or IPC mapping); nullptr at the ends of the slab stack
     double *lo_buf[2] = {nullptr, nullptr}, *hi_buf[2] = {nullptr, nullptr};
+    PTState *state = nullptr;                      // this slab's own PT state (z-slab stacks; cart handles share one per device)
+    unsigned long long *flags = nullptr;           // my halo flags [4][ntiles]
+    unsigned long long *lo_flags = nullptr, *hi_flags = nullptr;  // the z neighbours' flag arrays (local, peer or IPC pointers)
+    RankSlots **table = nullptr;                   // device array: every rank's mailbox (z-slab stacks)
     double *staging = nullptr;  // next job's state (b2s_diff3d_upload_state_async), allocated on first use
     double *stage_out = nullptr;  // device-side copy of a result on its way to the host (b2s_diff3d_download_state_async)
     bool staged = false, staging_used = false;
@@ -240,6 +252,9 @@ struct b2s_diff3d {
     int nslots_dst = 0;           // RankSlots instances that receive partials (devices in-process, ranks multi-process)
     bool multi = false;           // more than one slab in the global stack
     bool cart = false;            // decomposition in x or y as well: update_halo! as separate plane copies
+    bool zstack = false;          // multi && !cart: fused halo push with neighbour flags, lagged norm evaluation
+    int ntiles = 0;               // xy tiles per launch (= halo flags per array)
+    int skip_push = 0;            // host mirror of PTState::skip_push
     std::vector<char *> peer_base; // one process per GPU: every rank's arena (own or IPC-mapped), in rank order
     bool connected = false;       // multi-process: peers mapped
     std::vector<void *> ipc_mapped;
@@ -247,7 +262,8 @@ struct b2s_diff3d {
     unsigned long long seq = 1;   // host mirror of PTState::seq
     long long kernel_launches = 0;
     double last_ms = 0.0;
-    PTState *pinned = nullptr;    // host staging of the state
+    PTState *pinned = nullptr;    // host staging of the state: [0] upload, [1], [2] polled snapshots
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
     int it_step = 0;              // iter_inner of the time step in progress
 };
 
@@ -402,30 +418,44 @@ int launch_iteration(b2s_diff3d *h)
         p.mD_dx = -h->D_dx; p.mD_dy = -h->D_dy; p.mD_dz = -h->D_dz;
         p.norm_scale = h->prm.dt;
         p.partials = s.partials; p.ticket = s.ticket;
-        p.state = d.state;
+        p.state = h->zstack ? s.state : d.state;
         p.err_hist = d.err_hist;
         p.zchunk = h->zchunk;
         p.consistent = h->cfg.halo_mode == B2S_HALO_CONSISTENT;
         const size_t plane = (size_t)p.nx * p.ny;
         if (s.lo_buf[par ^ 1]) p.push_lo = s.lo_buf[par ^ 1] + plane * (p.nz - 1);
         if (s.hi_buf[par ^ 1]) p.push_hi = s.hi_buf[par ^ 1];
-        if (h->multi) {
+        if (h->zstack) {
+            p.peer_slots = s.table;
+            p.nranks = h->cfg.nslabs_total;
+            p.myrank = s.rank;
+            p.flagged = 1;
+            p.ntiles = h->ntiles;
+            p.flags = s.flags; p.lo_flags = s.lo_flags; p.hi_flags = s.hi_flags;
+            p.my_slots = s.slots;
+            p.timeout_cycles = (long long)20e9;
+        } else if (h->multi) {
             p.peer_slots = d.peer_table;
             p.nranks = h->nslots_dst;  // number of destinations
             p.myrank = s.rank;
         } else {
             p.fuse_finalize = 1;
         }
-        if (h->use_tma) B2S_CHECK(launch_tma(h->tma_choice, s.mapBuf[par], s.mapHt, p, d.stream));
-        else B2S_CHECK(launch_direct(p, d.stream));
+        p.array_arith = h->cfg.arithmetic == B2S_ARITH_ARRAY;
+        if (h->use_tma) {
+            B2S_CHECK(launch_tma(h->tma_choice, s.mapBuf[par], s.mapHt, p, d.stream));
+        } else {
+            ArrayArith aa = {1.0, h->prm.dx, h->prm.dy, h->prm.dz, h->prm.dt};
+            B2S_CHECK(launch_direct(p, d.stream, aa));
+        }
         h->kernel_launches += 1;
     }
     if (h->cart) B2S_CHECK(cart_update_halo(h, h->cfg.halo_mode == B2S_HALO_CONSISTENT ? (par ^ 1) : par));
-    if (h->multi) {
+    if (h->multi && !h->zstack) {
         for (DeviceCtx &d : h->devs) {
             B2S_CUDA(cudaSetDevice(d.dev));
             pt_finalize_kernel<<<1, kMaxRanks, 0, d.stream>>>(d.state, d.err_hist, nullptr, d.slots, h->cfg.nslabs_total,
-                                                              (long long)20e9);
+                                                              (long long)20e9, 0);
             B2S_CUDA(cudaGetLastError());
             h->kernel_launches += 1;
         }
@@ -437,6 +467,13 @@ int launch_iteration(b2s_diff3d *h)
 int upload_state(b2s_diff3d *h, const PTState &st)
 {
     *h->pinned = st;
+    if (h->zstack) {  // every slab of a z stack has its own state
+        for (Slab &s : h->slabs) {
+            B2S_CUDA(cudaSetDevice(s.dev));
+            B2S_CUDA(cudaMemcpyAsync(s.state, h->pinned, sizeof(PTState), cudaMemcpyHostToDevice, h->devs[s.devslot].stream));
+        }
+        return B2S_OK;
+    }
     for (DeviceCtx &d : h->devs) {
         B2S_CUDA(cudaSetDevice(d.dev));
         B2S_CUDA(cudaMemcpyAsync(d.state, h->pinned, sizeof(PTState), cudaMemcpyHostToDevice, d.stream));
@@ -444,7 +481,23 @@ int upload_state(b2s_diff3d *h, const PTState &st)
     return B2S_OK;
 }
 
+// z-slab stacks: one tiny kernel per slab at the end of a host batch evaluates the iteration the step kernels left pending
+int enqueue_lagged_finalize(b2s_diff3d *h)
+{
+    for (Slab &s : h->slabs) {
+        DeviceCtx &d = h->devs[s.devslot];
+        B2S_CUDA(cudaSetDevice(s.dev));
+        pt_finalize_kernel<<<1, kMaxRanks, 0, d.stream>>>(s.state, d.err_hist, nullptr, s.slots, h->cfg.nslabs_total, (long long)20e9, 1);
+        B2S_CUDA(cudaGetLastError());
+        h->kernel_launches += 1;
+    }
+    return B2S_OK;
+}
+
 // Runs the device-resident loop until the state says done. Returns the final state of device 0 in *out.
+// The host enqueues batches of iterations and polls one PTState per batch; the next batch is enqueued BEFORE the previous
+// one is polled (two pinned snapshots, two events), so the GPU never idles on the host round trip. Kernels enqueued after
+// the exit return at once.
 int run_loop(b2s_diff3d *h, PTState st, PTState *out)
 {
     B2S_REQUIRE(!h->multi || h->connected, B2S_ERR_STATE, "multi-process handle is not connected (b2s_diff3d_ipc_connect)");
@@ -453,6 +506,8 @@ int run_loop(b2s_diff3d *h, PTState st, PTState *out)
     st.total_iters = h->launched;
     st.seq = h->seq;
     st.error = 0;
+    st.pending = 0;
+    st.skip_push = h->skip_push;
     st.done = (st.it < st.iter_max) ? 0 : 1;
     B2S_CHECK(upload_state(h, st));
     for (DeviceCtx &d : h->devs) {
@@ -463,23 +518,38 @@ int run_loop(b2s_diff3d *h, PTState st, PTState *out)
     if (batch <= 0) {
         const double cells = (double)h->ar.cells;
         batch = cells >= 256.0 * 256 * 256 ? 16 : (cells >= 96.0 * 96 * 96 ? 64 : 128);
+        if (!st.check) batch = 512;  // fixed count: nothing to poll for but errors
     }
+    DeviceCtx &d0 = h->devs[0];
+    PTState *src = h->zstack ? h->slabs[0].state : d0.state;
     PTState cur = st;
-    while (!cur.done) {
-        const int remaining = cur.iter_max - cur.it;
-        const int n = std::min(batch, remaining);
-        const long long base = h->launched;
+    int enqueued = 0, inflight = 0, slot = 0;
+    auto submit = [&]() -> int {
+        const int n = std::min(batch, st.iter_max - st.it - enqueued);
+        if (n <= 0) return B2S_OK;
         for (int i = 0; i < n; ++i) B2S_CHECK(launch_iteration(h));
-        DeviceCtx &d0 = h->devs[0];
+        if (h->zstack) B2S_CHECK(enqueue_lagged_finalize(h));
         B2S_CUDA(cudaSetDevice(d0.dev));
-        B2S_CUDA(cudaMemcpyAsync(h->pinned + 1, d0.state, sizeof(PTState), cudaMemcpyDeviceToHost, d0.stream));
-        B2S_CUDA(cudaStreamSynchronize(d0.stream));
-        cur = h->pinned[1];
-        h->launched = cur.total_iters;  // launches after the exit were no-ops
-        h->seq = cur.seq;
-        (void)base;
-        B2S_REQUIRE(!cur.error, B2S_ERR_CUDA, "timed out waiting for a peer GPU's partial norm (iteration %d)", cur.it);
+        B2S_CUDA(cudaMemcpyAsync(h->pinned + 1 + slot, src, sizeof(PTState), cudaMemcpyDeviceToHost, d0.stream));
+        B2S_CUDA(cudaEventRecord(h->ev_poll[slot], d0.stream));
+        enqueued += n;
+        inflight += 1;
+        slot ^= 1;
+        return B2S_OK;
+    };
+    if (!cur.done) B2S_CHECK(submit());
+    while (inflight > 0) {
+        if (inflight < 2) B2S_CHECK(submit());      // keep one batch queued behind the one being waited for
+        const int oldest = inflight == 2 ? slot : slot ^ 1;
+        B2S_CUDA(cudaEventSynchronize(h->ev_poll[oldest]));
+        cur = h->pinned[1 + oldest];
+        inflight -= 1;
+        B2S_REQUIRE(!cur.error, B2S_ERR_CUDA, "timed out waiting for a peer GPU (halo flag or partial norm, iteration %d)", cur.it);
+        if (cur.done) break;  // everything still queued is a no-op
     }
+    h->launched = cur.total_iters;  // launches after the exit were no-ops (a speculative iteration is not counted)
+    h->seq = cur.seq;
+    h->skip_push = cur.skip_push;
     double ms_max = 0.0;
     for (DeviceCtx &d : h->devs) {
         B2S_CUDA(cudaSetDevice(d.dev));
@@ -551,6 +621,9 @@ int destroy_impl(b2s_diff3d *h)
         if (d.ev_staged_free) cudaEventDestroy(d.ev_staged_free);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
+    if (!h->devs.empty()) cudaSetDevice(h->devs[0].dev);
+    for (int i = 0; i < 2; ++i)
+        if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
     for (Slab &s : h->slabs) {
         cudaSetDevice(s.dev);
         if (s.arena) cudaFree(s.arena);
@@ -581,6 +654,9 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
     B2S_REQUIRE(cfg->halo_mode == B2S_HALO_REFERENCE_LAG2 || cfg->halo_mode == B2S_HALO_CONSISTENT, B2S_ERR_BAD_ARG,
                 "bad halo_mode");
     B2S_REQUIRE(cfg->bc_mode == B2S_BC_LITERAL || cfg->bc_mode == B2S_BC_PROPER, B2S_ERR_BAD_ARG, "bad bc_mode");
+    B2S_REQUIRE(cfg->arithmetic == B2S_ARITH_KERNEL || cfg->arithmetic == B2S_ARITH_ARRAY, B2S_ERR_BAD_ARG, "bad arithmetic");
+    B2S_REQUIRE(cfg->arithmetic == B2S_ARITH_KERNEL || cfg->kernel_variant != B2S_KERNEL_TMA, B2S_ERR_BAD_ARG,
+                "the array-programming arithmetic exists in the direct kernel only");
     {
         const int dx_ = cfg->dimx > 1 ? cfg->dimx : 1, dy_ = cfg->dimy > 1 ? cfg->dimy : 1;
         B2S_REQUIRE(cfg->dimx >= 0 && cfg->dimy >= 0 && cfg->nslabs_total % (dx_ * dy_) == 0, B2S_ERR_BAD_ARG,
@@ -609,7 +685,9 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
     compute_params(h);
     h->multi = cfg->nslabs_total > 1;
     h->cart = is_cart(*cfg);
-    h->ar.layout((size_t)cfg->nx * cfg->ny * cfg->nz);
+    h->zstack = h->multi && !h->cart;
+    // halo flags are sized for the finest tiling any kernel variant uses (64 x 4), so the arena layout does not depend on it
+    h->ar.layout((size_t)cfg->nx * cfg->ny * cfg->nz, (size_t)((cfg->nx + kDirBX - 1) / kDirBX) * ((cfg->ny + kDirBY - 1) / kDirBY));
 
 #define FAIL_IF(call)                      \
     do {                                   \
@@ -629,7 +707,7 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
         }                                                                                         \
     } while (0)
 
-    CUDA_FAIL_IF(cudaMallocHost(&h->pinned, 2 * sizeof(PTState)));
+    CUDA_FAIL_IF(cudaMallocHost(&h->pinned, 3 * sizeof(PTState)));
     // device contexts
     for (int i = 0; i < cfg->slab_count; ++i) {
         const int d = h->devices[i];
@@ -659,6 +737,9 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
         s.slots = (RankSlots *)(s.arena + h->ar.off_slots);
         s.partials = (double *)(s.arena + h->ar.off_partials);
         s.ticket = (unsigned int *)(s.arena + h->ar.off_ticket);
+        s.state = (PTState *)(s.arena + h->ar.off_state);
+        s.flags = (unsigned long long *)(s.arena + h->ar.off_flags);
+        s.table = (RankSlots **)(s.arena + h->ar.off_peer_table);
         h->slabs.push_back(s);
         DeviceCtx &dc = h->devs[slot];
         if (!dc.state) {
@@ -667,10 +748,12 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
             dc.peer_table = (RankSlots **)(s.arena + h->ar.off_peer_table);
         }
     }
+    CUDA_FAIL_IF(cudaSetDevice(h->devs[0].dev));
+    for (int i = 0; i < 2; ++i) CUDA_FAIL_IF(cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
     // kernel variant + geometry
     {
         const Slab &s0 = h->slabs[0];
-        const int kv = cfg->kernel_variant;
+        const int kv = cfg->arithmetic == B2S_ARITH_ARRAY ? B2S_KERNEL_DIRECT : cfg->kernel_variant;
         const bool elig = tma_eligible(cfg->nx, cfg->ny, cfg->nz, s0.Ht, s0.buf[0], s0.buf[1]);
         if (kv == B2S_KERNEL_TMA && !elig) {
             set_error("TMA variant needs even nx >= 64, ny >= 16, nz >= 8 (got %dx%dx%d)", cfg->nx, cfg->ny, cfg->nz);
@@ -681,7 +764,13 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
         if (h->use_tma) {
             h->tma_choice = tma_choice_index(h->ar.cells);
             const TmaChoice &c = kTmaChoices[h->tma_choice];
-            h->zchunk = pick_zchunk(((cfg->nx + c.tx - 1) / c.tx) * ((cfg->ny + c.ty - 1) / c.ty), cfg->nz, kMaxPartials);
+            h->ntiles = ((cfg->nx + c.tx - 1) / c.tx) * ((cfg->ny + c.ty - 1) / c.ty);
+            h->zchunk = pick_zchunk(h->ntiles, cfg->nz, kMaxPartials);
+            if (h->zchunk <= 0) {
+                set_error("grid %dx%dx%d has more xy tiles than the %d block partials", cfg->nx, cfg->ny, cfg->nz, kMaxPartials);
+                destroy_impl(h);
+                return B2S_ERR_BAD_SIZE;
+            }
             h->nblocks = grid_blocks_tma(h->tma_choice, cfg->nx, cfg->ny, cfg->nz, h->zchunk);
             for (Slab &s : h->slabs) {
                 CUDA_FAIL_IF(cudaSetDevice(s.dev));
@@ -690,7 +779,13 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
             }
         } else {
             const int tiles = ((cfg->nx + kDirBX - 1) / kDirBX) * ((cfg->ny + kDirBY - 1) / kDirBY);
+            h->ntiles = tiles;
             h->zchunk = pick_zchunk(tiles, cfg->nz, kMaxPartials);
+            if (h->zchunk <= 0) {
+                set_error("grid %dx%dx%d has more xy tiles than the %d block partials", cfg->nx, cfg->ny, cfg->nz, kMaxPartials);
+                destroy_impl(h);
+                return B2S_ERR_BAD_SIZE;
+            }
             h->nblocks = tiles * ((cfg->nz - 2 + h->zchunk - 1) / h->zchunk);
         }
     }
@@ -715,8 +810,17 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
         if (!h->cart) {  // z-slabs: the halo push is fused into the step kernel
             for (size_t i = 0; i < h->slabs.size(); ++i) {
                 Slab &s = h->slabs[i];
-                if (i > 0) { s.lo_buf[0] = h->slabs[i - 1].buf[0]; s.lo_buf[1] = h->slabs[i - 1].buf[1]; }
-                if (i + 1 < h->slabs.size()) { s.hi_buf[0] = h->slabs[i + 1].buf[0]; s.hi_buf[1] = h->slabs[i + 1].buf[1]; }
+                if (i > 0) { s.lo_buf[0] = h->slabs[i - 1].buf[0]; s.lo_buf[1] = h->slabs[i - 1].buf[1]; s.lo_flags = h->slabs[i - 1].flags; }
+                if (i + 1 < h->slabs.size()) {
+                    s.hi_buf[0] = h->slabs[i + 1].buf[0]; s.hi_buf[1] = h->slabs[i + 1].buf[1]; s.hi_flags = h->slabs[i + 1].flags;
+                }
+            }
+            // every slab publishes its partial norm into every slab's mailbox
+            std::vector<RankSlots *> all;
+            for (Slab &s : h->slabs) all.push_back(s.slots);
+            for (Slab &s : h->slabs) {
+                CUDA_FAIL_IF(cudaSetDevice(s.dev));
+                CUDA_FAIL_IF(cudaMemcpy(s.table, all.data(), sizeof(RankSlots *) * all.size(), cudaMemcpyHostToDevice));
             }
         } else {
             for (DeviceCtx &d : h->devs) {
@@ -724,12 +828,14 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
                 CUDA_FAIL_IF(cudaEventCreateWithFlags(&d.ev_bar, cudaEventDisableTiming));
             }
         }
-        std::vector<RankSlots *> tbl;
-        for (DeviceCtx &d : h->devs) tbl.push_back(d.slots);
-        h->nslots_dst = (int)tbl.size();
-        for (DeviceCtx &d : h->devs) {
-            CUDA_FAIL_IF(cudaSetDevice(d.dev));
-            CUDA_FAIL_IF(cudaMemcpy(d.peer_table, tbl.data(), sizeof(RankSlots *) * tbl.size(), cudaMemcpyHostToDevice));
+        if (h->cart) {
+            std::vector<RankSlots *> tbl;
+            for (DeviceCtx &d : h->devs) tbl.push_back(d.slots);
+            h->nslots_dst = (int)tbl.size();
+            for (DeviceCtx &d : h->devs) {
+                CUDA_FAIL_IF(cudaSetDevice(d.dev));
+                CUDA_FAIL_IF(cudaMemcpy(d.peer_table, tbl.data(), sizeof(RankSlots *) * tbl.size(), cudaMemcpyHostToDevice));
+            }
         }
         h->connected = true;
     }
@@ -769,6 +875,9 @@ int b2s_diff3d_set_initial(b2s_diff3d *h, const double *Ht_host)
     DeviceGuard guard;
     guard.set(h->devs[0].dev);
     const size_t n = h->ar.cells;
+    // Mailboxes, halo flags and the sequence number are never reset: they are monotonic, so a re-initialisation of a
+    // connected one-process-per-GPU handle cannot erase what a peer has already stored (the caller still has to put a
+    // barrier across the ranks between set_initial / init_gaussian and the first iteration, see b200stencil.h).
     for (size_t i = 0; i < h->slabs.size(); ++i) {
         Slab &s = h->slabs[i];
         DeviceCtx &d = h->devs[s.devslot];
@@ -776,13 +885,14 @@ int b2s_diff3d_set_initial(b2s_diff3d *h, const double *Ht_host)
         B2S_CUDA(cudaStreamSynchronize(d.stream));
         B2S_CUDA(cudaMemcpy(s.Ht, Ht_host + i * n, n * sizeof(double), cudaMemcpyHostToDevice));
         B2S_CUDA(cudaMemcpy(s.buf[0], s.Ht, n * sizeof(double), cudaMemcpyDeviceToDevice));  // Htau = copy(Ht)
-        B2S_CUDA(cudaMemset(s.buf[1], 0, n * sizeof(double)));                                 // Htau2 = @zeros
+        if (h->cfg.arithmetic == B2S_ARITH_ARRAY)  // in-place update of Htau (part1_array_programming.jl:17): the frame is Ht's forever
+            B2S_CUDA(cudaMemcpy(s.buf[1], s.Ht, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        else
+            B2S_CUDA(cudaMemset(s.buf[1], 0, n * sizeof(double)));                             // Htau2 = @zeros
         B2S_CUDA(cudaMemset(s.ticket, 0, 64));
-        B2S_CUDA(cudaMemset(s.slots, 0, sizeof(RankSlots)));
-        B2S_CUDA(cudaMemset(s.arena + h->ar.off_cart, 0, sizeof(CartSync)));
     }
     h->launched = 0;
-    h->seq = 1;
+    h->skip_push = 0;
     h->it_step = 0;
     return B2S_OK;
 }
@@ -883,8 +993,14 @@ int b2s_diff3d_ipc_connect(b2s_diff3d *h, const void *all_blobs, int nblobs)
         tbl[r] = (RankSlots *)(base + h->ar.off_slots);
         h->peer_base[r] = base;
         if (!h->cart) {  // z-slabs: the neighbours' buffers receive the fused halo push
-            if (r == s.rank - 1) { s.lo_buf[0] = (double *)(base + h->ar.off_buf[0]); s.lo_buf[1] = (double *)(base + h->ar.off_buf[1]); }
-            if (r == s.rank + 1) { s.hi_buf[0] = (double *)(base + h->ar.off_buf[0]); s.hi_buf[1] = (double *)(base + h->ar.off_buf[1]); }
+            if (r == s.rank - 1) {
+                s.lo_buf[0] = (double *)(base + h->ar.off_buf[0]); s.lo_buf[1] = (double *)(base + h->ar.off_buf[1]);
+                s.lo_flags = (unsigned long long *)(base + h->ar.off_flags);
+            }
+            if (r == s.rank + 1) {
+                s.hi_buf[0] = (double *)(base + h->ar.off_buf[0]); s.hi_buf[1] = (double *)(base + h->ar.off_buf[1]);
+                s.hi_flags = (unsigned long long *)(base + h->ar.off_flags);
+            }
         }
     }
     h->nslots_dst = nblobs;
@@ -895,19 +1011,6 @@ int b2s_diff3d_ipc_connect(b2s_diff3d *h, const void *all_blobs, int nblobs)
         B2S_CUDA(cudaMemcpy(s.arena + h->ar.off_cart_table, ct.data(), sizeof(CartSync *) * nblobs, cudaMemcpyHostToDevice));
     }
     h->connected = true;
-    return B2S_OK;
-}
-
-int b2s_diff3d_exchange_initial_halo(b2s_diff3d *h, int phase)
-{
-    // The fused exchange reproduces update_halo! from the first PT iteration on (diffusion3d_kernels.cuh), so no
-    // separate initial exchange exists in the reference semantics; kept as a synchronisation point of the ABI.
-    B2S_REQUIRE(h, B2S_ERR_BAD_ARG, "NULL handle");
-    (void)phase;
-    for (DeviceCtx &d : h->devs) {
-        B2S_CUDA(cudaSetDevice(d.dev));
-        B2S_CUDA(cudaStreamSynchronize(d.stream));
-    }
     return B2S_OK;
 }
 
@@ -1039,6 +1142,31 @@ int b2s_diff3d_gather(b2s_diff3d *h, double *H_g_host)
     return B2S_OK;
 }
 
+// A new job on an existing handle starts exactly like a fresh handle after set_initial (the reference allocates per run:
+// Htau = copy(Ht), Htau2 = @zeros, part1_kernel_programming.jl:141-142): Htau goes to buffer 0, the other buffer is
+// cleared, the ping-pong parity restarts. `src` (device) holds the new Ht. In a z-slab stack the halo planes of buffer 1
+// that a neighbour stores into are left alone: the neighbour's first kernel of the new job overwrites them before they
+// are read (with zeros in lag-2 mode -- the old content of its own cleared buffer --, with new values otherwise), and
+// clearing them here could race with that store.
+static int start_job_on_stream(b2s_diff3d *h, Slab &s, DeviceCtx &d, const double *src)
+{
+    const size_t bytes = h->ar.cells * sizeof(double);
+    if (src != s.Ht) B2S_CUDA(cudaMemcpyAsync(s.Ht, src, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    B2S_CUDA(cudaMemcpyAsync(s.buf[0], src, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    if (h->cfg.arithmetic == B2S_ARITH_ARRAY) {
+        B2S_CUDA(cudaMemcpyAsync(s.buf[1], src, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    } else {
+        const size_t plane = (size_t)h->cfg.nx * h->cfg.ny;
+        const size_t first = (h->zstack && s.lo_buf[1]) ? 1 : 0;
+        const size_t last = (h->zstack && s.hi_buf[1]) ? (size_t)h->cfg.nz - 2 : (size_t)h->cfg.nz - 1;
+        B2S_CUDA(cudaMemsetAsync(s.buf[1] + plane * first, 0, plane * (last - first + 1) * sizeof(double), d.stream));
+    }
+    h->launched = 0;
+    h->skip_push = 0;
+    h->it_step = 0;
+    return B2S_OK;
+}
+
 int b2s_diff3d_upload_state(b2s_diff3d *h, int slab, const double *Ht_host)
 {
     B2S_REQUIRE(h && Ht_host, B2S_ERR_BAD_ARG, "NULL argument");
@@ -1048,11 +1176,9 @@ int b2s_diff3d_upload_state(b2s_diff3d *h, int slab, const double *Ht_host)
     DeviceCtx &d = h->devs[s.devslot];
     DeviceGuard guard;
     guard.set(s.dev);
-    const int cur = (int)(h->launched & 1);
     const size_t bytes = h->ar.cells * sizeof(double);
     B2S_CUDA(cudaMemcpyAsync(s.Ht, Ht_host, bytes, cudaMemcpyHostToDevice, d.stream));
-    B2S_CUDA(cudaMemcpyAsync(s.buf[cur], s.Ht, bytes, cudaMemcpyDeviceToDevice, d.stream));
-    return B2S_OK;
+    return start_job_on_stream(h, s, d, s.Ht);
 }
 
 // copy stream + events of the pipelined transfers (created on first use)
@@ -1123,11 +1249,8 @@ int b2s_diff3d_commit_upload(b2s_diff3d *h, int slab)
     B2S_REQUIRE(s.staged, B2S_ERR_STATE, "no staged upload (call b2s_diff3d_upload_state_async first)");
     DeviceGuard guard;
     guard.set(s.dev);
-    const int cur = (int)(h->launched & 1);
-    const size_t bytes = h->ar.cells * sizeof(double);
     B2S_CUDA(cudaStreamWaitEvent(d.stream, d.ev_up, 0));
-    B2S_CUDA(cudaMemcpyAsync(s.Ht, s.staging, bytes, cudaMemcpyDeviceToDevice, d.stream));
-    B2S_CUDA(cudaMemcpyAsync(s.buf[cur], s.staging, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    B2S_CHECK(start_job_on_stream(h, s, d, s.staging));
     B2S_CUDA(cudaEventRecord(d.ev_staged_free, d.stream));
     s.staged = false;
     s.staging_used = true;

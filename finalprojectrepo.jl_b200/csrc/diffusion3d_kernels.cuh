@@ -23,23 +23,34 @@ struct PTState {
     int error;       // 1: cross-GPU wait timed out
     int hist_pos;    // next entry of err_hist
     int hist_cap;
-    int pad;
+    int pending;     // z-slab stacks: 1 = the iteration of the last executed step kernel has not been evaluated yet
     double tol;
     double err;
     double sumsq;          // global sum over ranks and cells of (R*dt)^2
     double sqrt_total_N;   // sqrt(prod(dims)*nx*ny*nz), part1_kernel_programming.jl:124,191
     long long total_iters; // PT iterations since create (selects the ping-pong parity)
     unsigned long long seq; // cross-GPU sequence number of the next partial to publish / consume
+    int skip_push;   // z-slab stacks, lag-2 halos: the next step kernel signals its halo flags without storing planes
+    int pad;
 };
 
 constexpr int kMaxRanks = 64;
+constexpr int kSlotGens = 4;
 
-// Cross-GPU (one process per GPU) reduction mailbox living in every rank's arena: peers store their partial and then
-// the sequence number. Two generations (seq parity) so a fast peer never overwrites an unread value.
+// Cross-GPU reduction mailbox living in every rank's arena: peers store their partial and then the sequence number.
+// Four generations (seq mod 4): with the lagged evaluation of z-slab stacks a rank publishes partial s+4 only after every
+// rank has finished kernel s+2, i.e. after partial s has been consumed everywhere (two generations suffice for the
+// per-iteration handshake of general decompositions).
 struct RankSlots {
-    double value[2][kMaxRanks];
-    unsigned long long seq[2][kMaxRanks];
+    double value[kSlotGens][kMaxRanks];
+    unsigned long long seq[kSlotGens][kMaxRanks];
 };
+
+// z-slab stacks: per-tile halo flags in every rank's arena, written by the two z neighbours (peer stores), read locally.
+// A flag holds the sequence number of the neighbour's step kernel that set it (monotonic, never reset).
+//   kFlagInLo / kFlagInHi  : the low / high neighbour has stored this tile of my plane 0 / nz-1          (data ready)
+//   kFlagAckLo / kFlagAckHi: the low / high neighbour has read the tile I stored into its plane nz-1 / 0 (free to overwrite)
+enum { kFlagInLo = 0, kFlagInHi = 1, kFlagAckLo = 2, kFlagAckHi = 3 };
 
 // General decompositions with one process per GPU: phase mailbox in every rank's arena. phase[r] is the last phase rank r
 // has completed (4*seq + k: k-th barrier of the PT iteration with sequence number seq), written by rank r itself.
@@ -71,6 +82,15 @@ struct StepParams {
     RankSlots *const *peer_slots;  // device array [nranks] of (peer-mapped) pointers, nullable
     int nranks, myrank;
     int zchunk;          // interior planes per block
+    // z-slab stacks (flagged protocol, see "Halo flags" below)
+    int flagged;                      // 1: neighbour flags + lagged evaluation of the norm
+    int ntiles;                       // xy tiles of this launch = flags per array
+    unsigned long long *flags;        // my 4 flag arrays [4][ntiles]
+    unsigned long long *lo_flags;     // low / high neighbour's flag arrays (peer-mapped), nullable
+    unsigned long long *hi_flags;
+    RankSlots *my_slots;              // my own mailbox (the last block consumes the previous iteration's partials)
+    long long timeout_cycles;
+    int array_arith;                  // 1: arithmetic of part1_array_programming.jl:9-18 (direct kernel only)
 };
 
 __device__ __forceinline__ void pt_finalize(PTState *s, double total, double *err_hist)
@@ -106,27 +126,137 @@ __device__ __forceinline__ double cell_residual_flux(double qx_lo, double qx_hi,
     return (qx_hi - qx_lo) * p._dx + (qy_hi - qy_lo) * p._dy + (qz_hi - qz_lo) * p._dz + (c - ht) * p._dt;
 }
 
+// ---- Halo flags: the z-slab protocol -----------------------------------------------------------------------------
+// No rank ever waits for ALL ranks on the critical path. Kernel number s (PTState::seq, identical on all ranks) of a rank
+//   * reads its halo planes 0 / nz-1 of Htau, which the neighbour's kernel s-1 has stored  -> wait in[t]  >= s-1  (RAW)
+//   * stores planes into the neighbour's Htau2 halo, which the neighbour's kernel s-1 read -> wait ack[t] >= s-1  (WAR)
+// per xy tile t, only in the blocks that own the first / last z chunk (they are scheduled first, so a neighbour that is
+// up to ~3/4 of a kernel behind never stalls anybody), and signals in[t] = s / ack[t] = s in the neighbour's arena when
+// the block is done (one __syncthreads, one system fence and <= 4 flag stores by one thread; no other block fences).
+// All waits refer to strictly earlier kernels, so every rank makes progress independently of co-residency.
+// The global norm is evaluated one kernel late: the last block of kernel s publishes its partial (as before) and then
+// consumes the partials of kernel s-1, which every rank published a whole kernel ago. If that test ends the PT loop,
+// kernel s was speculative: it is not counted, the ping-pong still holds the accepted state, and in lag-2 mode the next
+// executed kernel skips its plane stores (the speculative kernel has already forwarded exactly those values:
+// the old content of Htau2's boundary planes) -- bit-identical to the per-iteration handshake it replaces.
+__device__ __forceinline__ bool flag_wait(const unsigned long long *f, unsigned long long want, long long timeout)
+{
+    if (ld_acquire_sys_u64(f) >= want) return true;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(f) < want) {
+        if (clock64() - t0 > timeout) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
+// thread 0 of a boundary block, before any halo plane is read or any plane is stored into a neighbour
+__device__ __forceinline__ void halo_flags_wait(const StepParams &p, int tile, bool first_chunk, bool last_chunk,
+                                                unsigned long long seq)
+{
+    bool ok = true;
+    const unsigned long long want = seq - 1;
+    if (first_chunk && p.push_lo != nullptr) {
+        ok &= flag_wait(p.flags + (size_t)kFlagInLo * p.ntiles + tile, want, p.timeout_cycles);
+        ok &= flag_wait(p.flags + (size_t)kFlagAckLo * p.ntiles + tile, want, p.timeout_cycles);
+    }
+    if (last_chunk && p.push_hi != nullptr) {
+        ok &= flag_wait(p.flags + (size_t)kFlagInHi * p.ntiles + tile, want, p.timeout_cycles);
+        ok &= flag_wait(p.flags + (size_t)kFlagAckHi * p.ntiles + tile, want, p.timeout_cycles);
+    }
+    if (!ok) { p.state->error = 1; }
+    fence_proxy_async_all();  // the planes are fetched by TMA (async proxy) after this generic-proxy acquire
+}
+
+// all threads of a boundary block, after its last plane (the stores into the neighbours precede the flags)
+__device__ __forceinline__ void halo_flags_signal(const StepParams &p, int tile, bool first_chunk, bool last_chunk,
+                                                  unsigned long long seq, int tid)
+{
+    __syncthreads();
+    if (tid != 0) return;
+    __threadfence_system();
+    if (first_chunk && p.push_lo != nullptr) {
+        st_release_sys_u64(p.lo_flags + (size_t)kFlagInHi * p.ntiles + tile, seq);   // its plane nz-1 holds my tile
+        st_release_sys_u64(p.lo_flags + (size_t)kFlagAckHi * p.ntiles + tile, seq);  // I have read what it stored into my plane 0
+    }
+    if (last_chunk && p.push_hi != nullptr) {
+        st_release_sys_u64(p.hi_flags + (size_t)kFlagInLo * p.ntiles + tile, seq);
+        st_release_sys_u64(p.hi_flags + (size_t)kFlagAckLo * p.ntiles + tile, seq);
+    }
+}
+
+// boundary chunks first: grid z index -> z chunk
+__device__ __forceinline__ int chunk_of_block(const StepParams &p, int bz, int nchunks)
+{
+    if (!p.flagged) return bz;
+    return bz == 0 ? 0 : (bz == 1 ? nchunks - 1 : bz - 1);
+}
+
 // Shared tail of both kernel variants: block partial -> deterministic grid sum -> (optionally) exit test / publish.
-__device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, double *red)
+__device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, double *red, unsigned long long seq)
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nblocks = gridDim.x * gridDim.y * gridDim.z;
     const int bl = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     double bsum = block_sum(acc, red);
     double total = 0.0;
-    if (grid_sum_last_block(bsum, p.partials, p.ticket, nblocks, bl, red, &total)) {
+    if (!grid_sum_last_block_all(bsum, p.partials, p.ticket, nblocks, bl, red, &total)) return;
+    // ---- last block of the grid (all its threads; `total` is valid in thread 0) ----
+    if (tid == 0) {
         if (p.sumsq_out != nullptr) *p.sumsq_out = total;
         if (p.peer_slots != nullptr) {
-            const unsigned long long seq = p.state->seq;
-            const int g = (int)(seq & 1ull);
+            const unsigned long long sq = p.flagged ? seq : p.state->seq;
+            const int g = (int)(sq & (unsigned long long)(kSlotGens - 1));
             for (int r = 0; r < p.nranks; ++r) p.peer_slots[r]->value[g][p.myrank] = total;
             __threadfence_system();
-            for (int r = 0; r < p.nranks; ++r) st_release_sys_u64(&p.peer_slots[r]->seq[g][p.myrank], seq);
+            for (int r = 0; r < p.nranks; ++r) st_release_sys_u64(&p.peer_slots[r]->seq[g][p.myrank], sq);
         } else if (p.fuse_finalize) {
             pt_finalize(p.state, total, p.err_hist);
         }
     }
-    (void)tid;
+    if (!p.flagged) return;
+    // lagged evaluation: consume the partials of kernel seq-1 (published a whole kernel ago by every rank)
+    __shared__ double vals[kMaxRanks];
+    __shared__ int failed;
+    PTState *s = p.state;
+    const int pending = s->pending;  // uniform: only this block writes it, below
+    if (tid == 0) failed = 0;
+    __syncthreads();
+    if (pending) {
+        const unsigned long long want = seq - 1;
+        const int g1 = (int)(want & (unsigned long long)(kSlotGens - 1));
+        if (tid < p.nranks) {
+            const long long t0 = clock64();
+            bool ok = true;
+            while (ld_acquire_sys_u64(&p.my_slots->seq[g1][tid]) != want) {
+                if (clock64() - t0 > p.timeout_cycles) { ok = false; break; }
+                __nanosleep(32);
+            }
+            if (!ok) failed = 1;
+            vals[tid] = ld_relaxed_sys_f64(&p.my_slots->value[g1][tid]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (pending) {
+            if (failed) {
+                s->error = 1;
+                s->done = 1;
+            } else {
+                double t = 0.0;
+                for (int r = 0; r < p.nranks; ++r) t += vals[r];  // MPI.Allreduce!(+) in rank order
+                pt_finalize(s, t, p.err_hist);
+                if (s->done) {  // the loop ended with kernel seq-1: this kernel was speculative and is discarded
+                    s->pending = 0;
+                    s->skip_push = p.consistent ? 0 : 1;
+                }
+            }
+        } else {
+            s->pending = 1;
+            s->skip_push = 0;
+        }
+        s->seq = seq + 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -135,14 +265,33 @@ __device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, d
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDirBX = 64, kDirBY = 4;
 
-__global__ void __launch_bounds__(kDirBX *kDirBY) step_direct_kernel(const StepParams p)
+// Scalars of the array-programming arithmetic (part1_array_programming.jl:9-18), which divides by dx, dy, dz, dt where
+// the kernel version multiplies by reciprocals: q = D*d(Htau)/dx, dHdtau = -(Htau - Ht)/dt + (d(qx)/dx + d(qy)/dy + d(qz)/dz),
+// Htau += dHdtau*dtau. Evaluated in the reference's order; only the direct kernel has this mode (StepParams::array_arith).
+struct ArrayArith {
+    double D, dx, dy, dz, dt;
+};
+
+template <bool ARRAY>
+__global__ void __launch_bounds__(kDirBX *kDirBY) step_direct_kernel(const StepParams p, const ArrayArith aa)
 {
     __shared__ double red[32];
     if (p.state != nullptr && p.state->done) return;
+    const unsigned long long seq = p.flagged ? p.state->seq : 0ull;
+    const bool skip = p.flagged && p.state->skip_push;
     const int x = blockIdx.x * kDirBX + threadIdx.x;
     const int y = blockIdx.y * kDirBY + threadIdx.y;
-    const int zs = 1 + blockIdx.z * p.zchunk;
+    const int nchunks = gridDim.z;
+    const int zs = 1 + chunk_of_block(p, blockIdx.z, nchunks) * p.zchunk;
     const int ze = min(zs + p.zchunk, p.nz - 1);
+    const int tid = threadIdx.x + kDirBX * threadIdx.y;
+    const int tile = blockIdx.x + gridDim.x * blockIdx.y;
+    const bool first_chunk = zs == 1, last_chunk = ze == p.nz - 1;
+    const bool boundary = p.flagged && ((first_chunk && p.push_lo != nullptr) || (last_chunk && p.push_hi != nullptr));
+    if (boundary) {  // block-uniform
+        if (tid == 0) halo_flags_wait(p, tile, first_chunk, last_chunk, seq);
+        __syncthreads();
+    }
     const bool inb = x < p.nx && y < p.ny;
     const bool valid = x >= 1 && x <= p.nx - 2 && y >= 1 && y <= p.ny - 2;
     const size_t sy = (size_t)p.nx, sz = (size_t)p.nx * p.ny;
@@ -150,15 +299,25 @@ __global__ void __launch_bounds__(kDirBX *kDirBY) step_direct_kernel(const StepP
     if (inb) {
         size_t q = (size_t)x + sy * y + sz * zs;
         double zp = 0.0, c = 0.0;
-        if (valid) { zp = p.A[q - sz]; c = p.A[q]; }
+        // halo planes are written by the neighbour GPUs: read them past L1 (__ldcg)
+        if (valid) { zp = zs == 1 ? __ldcg(p.A + (q - sz)) : p.A[q - sz]; c = p.A[q]; }
         for (int z = zs; z < ze; ++z, q += sz) {
             const bool plo = p.push_lo != nullptr && z == 1;
             const bool phi = p.push_hi != nullptr && z == p.nz - 2;
             double outv = 0.0;
             if (plo || phi) outv = p.B[q];  // old content (also the value forwarded for boundary cells)
             if (valid) {
-                const double zn = p.A[q + sz];
-                const double r = cell_residual(c, p.A[q - 1], p.A[q + 1], p.A[q - sy], p.A[q + sy], zp, zn, p.Ht[q], p);
+                const double zn = z == p.nz - 2 ? __ldcg(p.A + (q + sz)) : p.A[q + sz];
+                double r;
+                if (ARRAY) {
+                    const double xl = p.A[q - 1], xr = p.A[q + 1], ys = p.A[q - sy], yn = p.A[q + sy];
+                    const double dH = -(c - p.Ht[q]) / aa.dt + ((aa.D * (xr - c) / aa.dx - aa.D * (c - xl) / aa.dx) / aa.dx +
+                                                                (aa.D * (yn - c) / aa.dy - aa.D * (c - ys) / aa.dy) / aa.dy +
+                                                                (aa.D * (zn - c) / aa.dz - aa.D * (c - zp) / aa.dz) / aa.dz);
+                    r = -dH;  // Htau + dHdtau*dtau == Htau - dtau*(-dHdtau) bit for bit; (-dH*dt)^2 == (dH*dt)^2
+                } else {
+                    r = cell_residual(c, p.A[q - 1], p.A[q + 1], p.A[q - sy], p.A[q + sy], zp, zn, p.Ht[q], p);
+                }
                 const double b = c - p.dtau * r;
                 p.B[q] = b;
                 if (p.R != nullptr) p.R[q] = r;
@@ -168,12 +327,12 @@ __global__ void __launch_bounds__(kDirBX *kDirBY) step_direct_kernel(const StepP
                 zp = c;
                 c = zn;
             }
-            if (plo) p.push_lo[(size_t)x + sy * y] = outv;
-            if (phi) p.push_hi[(size_t)x + sy * y] = outv;
+            if (plo && !skip) p.push_lo[(size_t)x + sy * y] = outv;
+            if (phi && !skip) p.push_hi[(size_t)x + sy * y] = outv;
         }
-        if (p.push_lo != nullptr || p.push_hi != nullptr) __threadfence_system();
     }
-    step_epilogue(p, acc, red);
+    if (boundary) halo_flags_signal(p, tile, first_chunk, last_chunk, seq, tid);
+    step_epilogue(p, acc, red, seq);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -203,6 +362,8 @@ __global__ void __launch_bounds__((TX / 2) * TY)
     extern __shared__ __align__(128) unsigned char smem_dyn[];  // TMA destinations need 128-byte alignment
     __shared__ double red[32];
     if (p.state != nullptr && p.state->done) return;
+    const unsigned long long seq = p.flagged ? p.state->seq : 0ull;
+    const bool skip = p.flagged && p.state->skip_push;
 
     // carve-up of the dynamic shared memory (kept in the shared state space: plain LDS/STS, no generic loads)
     double *sA = reinterpret_cast<double *>(smem_dyn);
@@ -211,14 +372,18 @@ __global__ void __launch_bounds__((TX / 2) * TY)
 
     const int tid = threadIdx.x + (TX / 2) * threadIdx.y;
     const int X0 = blockIdx.x * TX, Y0 = blockIdx.y * TY;
-    const int zs = 1 + blockIdx.z * p.zchunk;
+    const int zs = 1 + chunk_of_block(p, blockIdx.z, gridDim.z) * p.zchunk;
     const int ze = min(zs + p.zchunk, p.nz - 1);
     const int nplanes = (ze - zs) + 2;  // planes zs-1 .. ze
+    const int tile = blockIdx.x + gridDim.x * blockIdx.y;
+    const bool first_chunk = zs == 1, last_chunk = ze == p.nz - 1;
+    const bool boundary = p.flagged && ((first_chunk && p.push_lo != nullptr) || (last_chunk && p.push_hi != nullptr));
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
         fence_proxy_async();
+        if (boundary) halo_flags_wait(p, tile, first_chunk, last_chunk, seq);
     }
     __syncthreads();
 
@@ -297,16 +462,16 @@ __global__ void __launch_bounds__((TX / 2) * TY)
         }
         if (valid0) { const double v = r0 * p.norm_scale; acc += v * v; }
         if (valid1) { const double v = r1 * p.norm_scale; acc += v * v; }
-        if (plo) { if (inb0) p.push_lo[pxy] = o0; if (inb1) p.push_lo[pxy + 1] = o1; }
-        if (phi) { if (inb0) p.push_hi[pxy] = o0; if (inb1) p.push_hi[pxy + 1] = o1; }
+        if (plo && !skip) { if (inb0) p.push_lo[pxy] = o0; if (inb1) p.push_lo[pxy + 1] = o1; }
+        if (phi && !skip) { if (inb0) p.push_hi[pxy] = o0; if (inb1) p.push_hi[pxy + 1] = o1; }
 
         __syncthreads();  // every thread is done with stage stc -> refill it
         if (tid == 0 && q - 1 + S < nplanes) issue(q - 1 + S);
         aprev = acur;
         acur = anext;
     }
-    if (p.push_lo != nullptr || p.push_hi != nullptr) __threadfence_system();
-    step_epilogue(p, acc, red);
+    if (boundary) halo_flags_signal(p, tile, first_chunk, last_chunk, seq, tid);
+    step_epilogue(p, acc, red, seq);
 }
 
 // update_halo! of a general Cartesian decomposition (ImplicitGlobalGrid): one plane of `src` (index sp along `axis`) is
@@ -356,20 +521,22 @@ __global__ void cart_barrier_kernel(PTState *state, CartSync *mine, CartSync *co
 }
 
 // One block: consume the partial sums of all ranks in rank order (deterministic, identical on every GPU).
-// In-process handles pass `local` (nranks contiguous doubles on this device); one-process-per-GPU handles pass `slots`
-// and wait (bounded) for the peers' stores.
+// In-process handles pass `local` (nranks contiguous doubles on this device); otherwise `slots` is waited on (bounded).
+// lagged = 0 (general decompositions): once per PT iteration, consumes the partials of kernel `seq` and advances seq.
+// lagged = 1 (z-slab stacks): once per host batch, evaluates the one iteration the step kernels have left pending.
 __global__ void pt_finalize_kernel(PTState *state, double *err_hist, const double *local, RankSlots *slots, int nranks,
-                                   long long timeout_cycles)
+                                   long long timeout_cycles, int lagged)
 {
     if (state->done) return;
+    if (lagged && !state->pending) return;
     __shared__ double vals[kMaxRanks];
     __shared__ int failed;
     const int t = threadIdx.x;
     if (t == 0) failed = 0;
     __syncthreads();
     if (slots != nullptr) {
-        const unsigned long long seq = state->seq;
-        const int g = (int)(seq & 1ull);
+        const unsigned long long seq = lagged ? state->seq - 1 : state->seq;
+        const int g = (int)(seq & (unsigned long long)(kSlotGens - 1));
         if (t < nranks) {
             const long long t0 = clock64();
             bool ok = true;
@@ -391,7 +558,8 @@ __global__ void pt_finalize_kernel(PTState *state, double *err_hist, const doubl
         } else {
             double total = 0.0;
             for (int r = 0; r < nranks; ++r) total += vals[r];  // MPI.Allreduce!(+) in rank order
-            state->seq += 1;
+            if (lagged) state->pending = 0;
+            else state->seq += 1;
             pt_finalize(state, total, err_hist);
         }
     }

@@ -1,10 +1,11 @@
 """Host-side mirror of scripts-part1 of the reference (same names, argument meaning and return values), on top of
 the C ABI of libb200stencil.so.  The reference's host language is Julia, which is absent from this image; the Julia
-shims (julia/part1_b200.jl) bind the same symbols with ccall and have the same structure as this file.
+module (julia/B200Stencil.jl) binds the same symbols with ccall and has the same structure as this file.
 
 Mirrored entry points (reference file:line):
   diffusion_3D_kernel_programming   scripts-part1/part1_kernel_programming.jl:99-228
-  diffusion_3D_array_programming    scripts-part1/part1_array_programming.jl:20-92  (alias: consistent halo mode)
+  diffusion_3D_array_programming    scripts-part1/part1_array_programming.jl:20-92  (B2S_ARITH_ARRAY: its own arithmetic,
+                                    in-place update of Htau, consistent halos)
   BenchResults                      scripts-part1/part1_kernel_programming.jl:22-29
   main (CLI)                        scripts-part1/part1.jl:25-60
 """
@@ -28,7 +29,7 @@ class Diffusion3D:
 
     def __init__(self, nx, ny, nz, nslabs=1, devices=None, slab_begin=0, slab_count=None,
                  halo_mode=capi.HALO_REFERENCE_LAG2, bc_mode=capi.BC_LITERAL, scale_physical_size=False,
-                 kernel_variant=capi.KERNEL_AUTO, batch=0, dims=None):
+                 kernel_variant=capi.KERNEL_AUTO, batch=0, dims=None, arithmetic=capi.ARITH_KERNEL):
         """dims = (dimx, dimy, dimz): general Cartesian rank grid like init_global_grid's (ranks in MPI Cartesian order,
         z fastest; in-process or one process per GPU). Default: z-slabs (1, 1, nslabs)."""
         self._L = capi.lib()
@@ -48,7 +49,8 @@ class Diffusion3D:
         self._devs = (C.c_int * self.slab_count)(*devices)
         cfg = capi.Diff3DConfig(self.n[0], self.n[1], self.n[2], self.nslabs, self.slab_begin, self.slab_count,
                                 C.cast(self._devs, C.POINTER(C.c_int)), halo_mode, bc_mode,
-                                int(bool(scale_physical_size)), kernel_variant, batch, self.dims[0], self.dims[1])
+                                int(bool(scale_physical_size)), kernel_variant, batch, self.dims[0], self.dims[1],
+                                int(arithmetic))
         self._h = C.c_void_p()
         capi.check(self._L.b2s_diff3d_create(C.byref(self._h), C.byref(cfg)))
         p = capi.Diff3DParams()
@@ -167,7 +169,8 @@ class Diffusion3D:
 def diffusion_3D_kernel_programming(*, nx, ny, nz, ttot=1.0, tol=1e-8, use_shared_memory=True, do_vis=False,
                                     verbose=True, init_and_finalize_MPI=True, scale_physical_size=False, nslabs=1,
                                     devices=None, halo_mode=capi.HALO_REFERENCE_LAG2, bc_mode=capi.BC_LITERAL,
-                                    kernel_variant=capi.KERNEL_AUTO, return_iters=False, dims=None):
+                                    kernel_variant=capi.KERNEL_AUTO, return_iters=False, dims=None,
+                                    arithmetic=capi.ARITH_KERNEL):
     """Drop-in for scripts-part1/part1_kernel_programming.jl:99.  Returns (X_g, H_g, BenchResults).
 
     `use_shared_memory` selects the staged (TMA) or the direct kernel; results are bit-identical either way.
@@ -182,7 +185,7 @@ def diffusion_3D_kernel_programming(*, nx, ny, nz, ttot=1.0, tol=1e-8, use_share
     if kv == capi.KERNEL_AUTO and not use_shared_memory:
         kv = capi.KERNEL_DIRECT
     s = Diffusion3D(nx, ny, nz, nslabs=nslabs, devices=devices, halo_mode=halo_mode, bc_mode=bc_mode,
-                    scale_physical_size=scale_physical_size, kernel_variant=kv, dims=dims)
+                    scale_physical_size=scale_physical_size, kernel_variant=kv, dims=dims, arithmetic=arithmetic)
     try:
         s.init_gaussian()
         iter_max = 100000  # :130
@@ -203,8 +206,9 @@ def diffusion_3D_kernel_programming(*, nx, ny, nz, ttot=1.0, tol=1e-8, use_share
             timed_iter_total += it
             iters.append(it)
             s.advance_time()
-        H_g = s.gather()  # also synchronises
-        dt_wall = time.time() - tic
+        s.sync()
+        dt_wall = time.time() - tic  # toc() comes before gather! in the reference (:206,223)
+        H_g = s.gather()
         cells = (nx - 2) * (ny - 2) * (nz - 2)
         work = float(nslabs) * timed_iter_total * (25 + 2) * cells  # :210
         mem = float(nslabs) * timed_iter_total * ((6 + 1) if use_shared_memory else (14 + 1)) * 8 * cells  # :212-214
@@ -212,7 +216,7 @@ def diffusion_3D_kernel_programming(*, nx, ny, nz, ttot=1.0, tol=1e-8, use_share
                            work / mem if mem else float("nan"), mem / dt_wall if dt_wall > 0 else float("nan"))
         if verbose:
             print(f"Finished after {nt - 2} outer iterations in {dt_wall:3.3f} seconds of compute!")
-        X_g = np.linspace(0 + s.dx / 2, s.lx - s.dx / 2, nx)  # LinRange(..., nx*dims[1]); dims[1] == 1 for z-slabs
+        X_g = np.linspace(0 + s.dx / 2, s.lx - s.dx / 2, nx * s.dims[0])  # LinRange(dx/2, lx-dx/2, nx*dims[1]), :221
         if return_iters:
             return X_g, H_g, res, iters
         return X_g, H_g, res
@@ -221,11 +225,13 @@ def diffusion_3D_kernel_programming(*, nx, ny, nz, ttot=1.0, tol=1e-8, use_share
 
 
 def diffusion_3D_array_programming(*, nx, ny, nz, do_vis=False, verbose=True, init_and_finalize_MPI=True, nslabs=1,
-                                   devices=None):
-    """Drop-in for scripts-part1/part1_array_programming.jl:20 (ttot = 1, tol = 1e-8 hard-wired there, :31-40):
-    the same update with the consistent halo exchange of :66-67.  Returns (X_g, H_g)."""
+                                   devices=None, dims=None):
+    """Drop-in for scripts-part1/part1_array_programming.jl:20 (ttot = 1, tol = 1e-8 hard-wired there, :23,39): the array
+    version's own arithmetic (:9-18: q = D*d(Htau)/dx, divisions instead of reciprocals), Htau updated in place (its frame
+    keeps Ht's values) and update_halo!(Htau) after the update (:66-67).  Returns (X_g, H_g)."""
     X_g, H_g, _ = diffusion_3D_kernel_programming(nx=nx, ny=ny, nz=nz, ttot=1.0, tol=1e-8, verbose=verbose, nslabs=nslabs,
-                                                  devices=devices, halo_mode=capi.HALO_CONSISTENT)
+                                                  devices=devices, halo_mode=capi.HALO_CONSISTENT, dims=dims,
+                                                  arithmetic=capi.ARITH_ARRAY)
     return X_g, H_g
 
 

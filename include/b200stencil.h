@@ -65,6 +65,10 @@ int b2s_shutdown(void);
 #define B2S_KERNEL_AUTO 0
 #define B2S_KERNEL_DIRECT 1 /* one thread per cell pair, neighbours through L1/L2 (reference-shaped; correctness anchor) */
 #define B2S_KERNEL_TMA 2    /* 2.5-D z-marching, TMA-staged planes in an mbarrier ring, register z-queue */
+/* Arithmetic of the PT update. */
+#define B2S_ARITH_KERNEL 0 /* part1_kernel_programming.jl:12-20,46-58: fluxes with D_dx = D/dx, residual with _dx = 1/dx */
+#define B2S_ARITH_ARRAY 1  /* part1_array_programming.jl:9-18: q = D*d(Htau)/dx, divisions by dx, dy, dz, dt, Htau updated in
+                            * place (its frame keeps Ht's values); direct kernel only */
 
 /*
  * L0: one launch of the fused flux/residual/update kernel.
@@ -98,8 +102,9 @@ typedef struct {
     int dimx, dimy;          /* general Cartesian decomposition dims = (dimx, dimy, nslabs_total/(dimx*dimy)) like
                               * ImplicitGlobalGrid's init_global_grid (part1_kernel_programming.jl:117); 0 or 1 = z-slabs.
                               * Rank r has coords (r / (dimy*dimz), (r / dimz) % dimy, r % dimz) (MPI Cartesian order).
-                              * dimx*dimy > 1 needs an in-process handle (slab_count == nslabs_total); update_halo! then
-                              * runs as separate plane copies in ImplicitGlobalGrid's order x, y, z after every step. */
+                              * update_halo! then runs as separate plane copies in ImplicitGlobalGrid's order x, y, z after
+                              * every step (in-process or one process per GPU). */
+    int arithmetic;          /* B2S_ARITH_* (0 = the kernel-programming version) */
 } b2s_diff3d_config;
 
 /* Derived numerics of part1_kernel_programming.jl:117-152. */
@@ -118,7 +123,9 @@ int b2s_diff3d_params_for(const b2s_diff3d_config *cfg, b2s_diff3d_params *out);
 /* Ht = init_local_gaussian; apply_boundary_conditions!; Htau = copy(Ht); Htau2 = 0
  * (part1_kernel_programming.jl:137-142, part1_utils.jl:1-34). Evaluated on the host like the reference. */
 int b2s_diff3d_init_gaussian(b2s_diff3d *h);
-/* Same, from caller-provided LOCAL arrays (host, nx*ny*nz per hosted slab, slab-major). */
+/* Same, from caller-provided LOCAL arrays (host, nx*ny*nz per hosted slab, slab-major).
+ * One process per GPU: every rank initialises, then b2s_diff3d_ipc_connect, then a barrier across the ranks (the caller's:
+ * MPI / torch.distributed) before the first iteration; a later re-initialisation needs the same barrier after it. */
 int b2s_diff3d_set_initial(b2s_diff3d *h, const double *Ht_host);
 
 /* Multi-process z-slabs (one process per GPU): export the CUDA IPC handles of this handle's halo mailboxes and
@@ -127,10 +134,8 @@ int b2s_diff3d_set_initial(b2s_diff3d *h, const double *Ht_host);
 size_t b2s_diff3d_ipc_blob_bytes(void);
 int b2s_diff3d_ipc_export(b2s_diff3d *h, void *blob_out);
 int b2s_diff3d_ipc_connect(b2s_diff3d *h, const void *all_blobs, int nblobs);
-/* After connect (or directly for in-process handles): seeds the halo mailboxes from the neighbours' initial
- * planes. phase 0 = everything (in-process handles only); multi-process: phase 1 (push own boundary planes to
- * the neighbours), barrier across ranks (caller's job), phase 2 (local fix-up), barrier. */
-int b2s_diff3d_exchange_initial_halo(b2s_diff3d *h, int phase);
+/* There is no separate initial halo exchange: the reference has none either (update_halo! only runs inside the PT loop,
+ * part1_kernel_programming.jl:182,187) and the fused exchange reproduces it from the first iteration on. */
 
 /* while err > tol && iter < iter_max  (part1_kernel_programming.jl:177-193) -- device-resident loop:
  * the exit test runs on the GPU, the host polls a flag once per batch.  iters/err are the reference's
@@ -150,8 +155,11 @@ int b2s_diff3d_get_field(b2s_diff3d *h, int slab, int which, double *host_out);
 int b2s_diff3d_gather(b2s_diff3d *h, double *H_g_host);
 /* Device pointers of a hosted slab (for zero-copy interop): which as in get_field. */
 int b2s_diff3d_device_ptr(b2s_diff3d *h, int slab, int which, double **dev_out);
-/* Host<->device transfer of the evolving state through the public API (used by the end-to-end benchmark):
- * uploads Ht and Htau (Htau := Ht) from host memory / downloads Htau. */
+/* Host<->device transfer of the evolving state through the public API (used by the end-to-end benchmark).
+ * upload_state starts a NEW JOB on the handle: Ht := host data, Htau := Ht, Htau2 := 0, ping-pong parity reset -- the
+ * state of a fresh handle after set_initial, so a job's result does not depend on what ran before (call it for every
+ * hosted slab; one process per GPU: all ranks must have returned from the previous job's last call first, which
+ * solve_timestep / iterate guarantee because their final norm needs every rank). download_state copies Htau out. */
 int b2s_diff3d_upload_state(b2s_diff3d *h, int slab, const double *Ht_host);
 int b2s_diff3d_download_state(b2s_diff3d *h, int slab, double *Htau_host);
 /* Pipelined variant for back-to-back jobs: the result is copied aside on the device (an extra nx*ny*nz array, allocated

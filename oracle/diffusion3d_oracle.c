@@ -13,6 +13,7 @@
  *   scripts-part1/part1_utils.jl:1-12                 init_local_gaussian
  *   scripts-part1/part1_utils.jl:14-34                apply_boundary_conditions!
  *   scripts-part1/part1_utils.jl:36-40                dist_norm_L2
+ *   scripts-part1/part1_array_programming.jl:9-18,61-83  array-programming version (orc_diff3d_set_array)
  * Un-vendored upstream behaviour restated (ImplicitGlobalGrid.jl, unpinned):
  *   overlap 2, nx_g = dims*(n-2)+2, x_g = (coords*(n-2)+i)*dx (0-based i),
  *   update_halo! per axis in order x,y,z on whole planes, 0-based coords.
@@ -43,6 +44,8 @@ typedef struct {
     int nranks;
     int halo_mode, bc_mode;
     int unfused_norm;    /* 1: materialise R*dt and (.)^2 temporaries like the reference (timing structure) */
+    int array;           /* 1: the array-programming version (in-place update of Htau, flux arrays, divisions) */
+    double *qx, *qy, *qz; /* its flux arrays (nx-1)(ny-2)(nz-2), (nx-2)(ny-1)(nz-2), (nx-2)(ny-2)(nz-1) */
     double lx, ly, lz, dx, dy, dz, dt, dtau;
     double _dt, _dx, _dy, _dz, D_dx, D_dy, D_dz;
     double total_N;
@@ -75,6 +78,7 @@ void orc_diff3d_destroy(orc_diff3d *s)
         if (s->R) free(s->R[r]);
     }
     free(s->Ht); free(s->A); free(s->B); free(s->R); free(s->tmp1); free(s->tmp2);
+    free(s->qx); free(s->qy); free(s->qz);
     free(s);
 }
 
@@ -174,6 +178,64 @@ static void step_tau_rank(const orc_diff3d *s, const double *restrict Ht, const 
         }
 }
 
+/* Switches the solver to diffusion_3D_array_programming (part1_array_programming.jl:20-92): update_halo!(Htau) after the
+ * in-place update (:66-67), i.e. consistent halos. Call right after create. */
+void orc_diff3d_set_array(orc_diff3d *s)
+{
+    s->array = 1;
+    s->halo_mode = ORC_HALO_CONSISTENT;
+    s->qx = (double *)calloc((size_t)(s->nx - 1) * (s->ny - 2) * (s->nz - 2), sizeof(double));
+    s->qy = (double *)calloc((size_t)(s->nx - 2) * (s->ny - 1) * (s->nz - 2), sizeof(double));
+    s->qz = (double *)calloc((size_t)(s->nx - 2) * (s->ny - 2) * (s->nz - 1), sizeof(double));
+}
+
+/* part1_array_programming.jl:9-18 with the statements as whole-array operations (the order in which the course's
+ * array-programming model defines them): all of qx, qy, qz from the current Htau, then dHdtau on the inner points, then
+ * the in-place update @inn(Htau) += dHdtau*dtau. R receives dHdtau at the inner points (its frame stays 0), so that
+ * dist_norm_L2(dHdt*dt) (:68) is the same sum as in the kernel version. */
+static void array_step_rank(const orc_diff3d *s, const double *restrict Ht, double *restrict H, double *restrict R)
+{
+    const int nx = s->nx, ny = s->ny, nz = s->nz;
+    const size_t sy = nx, sz = (size_t)nx * ny;
+    const double D = 1.0, dx = s->dx, dy = s->dy, dz = s->dz, dt = s->dt, dtau = s->dtau;
+    double *qx = s->qx, *qy = s->qy, *qz = s->qz;
+    const size_t ax = nx - 1, bx = nx - 2, ay = ny - 2, by = ny - 1;
+    /* @all(qx) = D * @d_xi(Htau) / dx  : d_xi = differences in x of the y,z-inner points */
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz - 2; ++k)
+        for (int j = 0; j < ny - 2; ++j)
+            for (int i = 0; i < nx - 1; ++i) {
+                size_t p = (size_t)i + sy * (j + 1) + sz * (k + 1);
+                qx[i + ax * (j + ay * k)] = D * (H[p + 1] - H[p]) / dx;
+            }
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz - 2; ++k)
+        for (int j = 0; j < ny - 1; ++j)
+            for (int i = 0; i < nx - 2; ++i) {
+                size_t p = (size_t)(i + 1) + sy * j + sz * (k + 1);
+                qy[i + bx * (j + by * k)] = D * (H[p + sy] - H[p]) / dy;
+            }
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz - 1; ++k)
+        for (int j = 0; j < ny - 2; ++j)
+            for (int i = 0; i < nx - 2; ++i) {
+                size_t p = (size_t)(i + 1) + sy * (j + 1) + sz * k;
+                qz[i + bx * (j + ay * k)] = D * (H[p + sz] - H[p]) / dz;
+            }
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz - 2; ++k)
+        for (int j = 0; j < ny - 2; ++j)
+            for (int i = 0; i < nx - 2; ++i) {
+                size_t p = (size_t)(i + 1) + sy * (j + 1) + sz * (k + 1);
+                double dH = -(H[p] - Ht[p]) / dt +
+                            ((qx[(i + 1) + ax * (j + ay * k)] - qx[i + ax * (j + ay * k)]) / dx +
+                             (qy[i + bx * ((j + 1) + by * k)] - qy[i + bx * (j + by * k)]) / dy +
+                             (qz[i + bx * (j + ay * (k + 1))] - qz[i + bx * (j + ay * k)]) / dz);
+                R[p] = dH;
+                H[p] = H[p] + dH * dtau;
+            }
+}
+
 /* sum((R*dt).^2) over the whole local array; per-plane partials combined in plane order. */
 static double sumsq_rank(const orc_diff3d *s, const double *restrict R)
 {
@@ -250,9 +312,14 @@ static void update_halo(const orc_diff3d *s, double **F)
 double orc_diff3d_iterate_once(orc_diff3d *s)
 {
     double sq = 0.0;
-    for (int r = 0; r < s->nranks; ++r) step_tau_rank(s, s->Ht[r], s->A[r], s->B[r], s->R[r]);
-    update_halo(s, s->halo_mode == ORC_HALO_REFERENCE_LAG2 ? s->A : s->B);
-    double **t = s->A; s->A = s->B; s->B = t;
+    if (s->array) { /* part1_array_programming.jl:65-68: step in place, update_halo!(Htau), norm */
+        for (int r = 0; r < s->nranks; ++r) array_step_rank(s, s->Ht[r], s->A[r], s->R[r]);
+        update_halo(s, s->A);
+    } else {
+        for (int r = 0; r < s->nranks; ++r) step_tau_rank(s, s->Ht[r], s->A[r], s->B[r], s->R[r]);
+        update_halo(s, s->halo_mode == ORC_HALO_REFERENCE_LAG2 ? s->A : s->B);
+        double **t = s->A; s->A = s->B; s->B = t;
+    }
     for (int r = 0; r < s->nranks; ++r) sq += sumsq_rank(s, s->R[r]); /* MPI.Allreduce!(+) in rank order */
     s->iters_total += 1;
     return sqrt(sq) / sqrt(s->total_N);

@@ -75,6 +75,8 @@ def lib():
         L.orc_diff3d_get.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
         L.orc_diff3d_gather.argtypes = [C.c_void_p, _dp]
         L.orc_diff3d_params.argtypes = [C.c_void_p, _dp]
+        L.orc_diff3d_set_array.argtypes = [C.c_void_p]
+        L.orc_diff3d_set_array.restype = None
         L.orc_diff3d_num_timesteps.restype = C.c_int
         L.orc_diff3d_num_timesteps.argtypes = [C.c_double, C.c_double]
         L.orc_diff3d_run.restype = C.c_long
@@ -133,12 +135,15 @@ class Diffusion3D:
     """Emulated-rank oracle of diffusion_3D_kernel_programming (scripts-part1/part1_kernel_programming.jl:99)."""
 
     def __init__(self, nx, ny, nz, dims=(1, 1, 1), halo_mode=HALO_REFERENCE_LAG2, bc_mode=BC_LITERAL,
-                 scale_physical_size=False, unfused_norm=False):
+                 scale_physical_size=False, unfused_norm=False, array=False):
+        """array=True: diffusion_3D_array_programming (scripts-part1/part1_array_programming.jl:20) instead."""
         self.L = lib()
         self.n = (nx, ny, nz)
         self.dims = tuple(dims)
         self.h = self.L.orc_diff3d_create(nx, ny, nz, dims[0], dims[1], dims[2], halo_mode, bc_mode,
                                           int(scale_physical_size), int(unfused_norm))
+        if array:
+            self.L.orc_diff3d_set_array(self.h)
         p = np.zeros(8)
         self.L.orc_diff3d_params(self.h, p.ctypes.data_as(_dp))
         self.dx, self.dy, self.dz, self.dt, self.dtau, self.lx, self.ly, self.lz = p

@@ -334,3 +334,91 @@ def test_c_level_run_set_initial_state_io_and_device_ptrs(b2s, gpu, oracle):
     err = np.sqrt(tS.item()) / np.sqrt(g.total_N)
     assert abs(err - e_ref[0]) <= REL_NORM_TOL * err
     g.close(); ref.close()
+
+
+def test_512_tma_headline_instantiation_vs_oracle(b2s, gpu, oracle):
+    """The <128,8,4> TMA instantiation the headline benchmark runs (512^3, BASELINE configs[2]) against the oracle itself:
+    3 PT iterations, every cell of Htau and Htau2 bit-exact, the norm within 1e-12 relative."""
+    from b200stencil import capi
+    n = (512, 512, 512)
+    o = oracle.Diffusion3D(*n)
+    g = _mk(b2s, *n, kernel_variant=capi.KERNEL_TMA)
+    g.init_gaussian()
+    eo, eg = o.iterate(3), g.iterate(3)
+    assert np.allclose(eg, eo, rtol=REL_NORM_TOL, atol=0)
+    assert np.array_equal(g.get("Htau"), o.get("Htau"))
+    assert np.array_equal(g.get("Htau2"), o.get("Htau2"))
+    g.close()
+
+
+def test_array_programming_variant(b2s, gpu, oracle):
+    """D-8: diffusion_3D_array_programming (part1_array_programming.jl:20) -- test/part1.jl:24 runs it at 32^3 against
+    test_1.bson (atol 1e-5); here also bit-exact against the oracle's restatement of the array version (its own
+    arithmetic, in-place update: the frame of Htau keeps Ht's values) and with the same PT iteration counts."""
+    from b200stencil import capi, part1
+    X, H = part1.diffusion_3D_array_programming(nx=32, ny=32, nz=32, verbose=False)
+    gold = json.load(open(os.path.join(GOLDEN, "part1_test_1.json")))
+    inds = [int(np.ceil(v)) - 1 for v in np.linspace(1, len(X), 12)]  # test/part1.jl:25
+    Hs = H[np.ix_(inds, inds, [14])][:, :, 0]
+    Href = np.array(gold["H"]["data_column_major"]).reshape(gold["H"]["size"], order="F")
+    assert np.allclose(Hs, Href, atol=1e-5, rtol=0)
+    assert np.allclose(X[inds], np.array(gold["X"]["data_column_major"]), atol=1e-5, rtol=0)
+    o = oracle.Diffusion3D(32, 32, 32, array=True)
+    assert o.run(ttot=1.0, tol=1e-8) == [188, 187, 185, 184, 183]
+    assert np.array_equal(H, o.gather())
+    # per-iteration parity incl. two emulated ranks (update_halo!(Htau) after the in-place update)
+    for nslabs in (1, 2):
+        oo = oracle.Diffusion3D(40, 24, 18, dims=(1, 1, nslabs), array=True)
+        g = _mk(b2s, 40, 24, 18, nslabs=nslabs, devices=[0] * nslabs, halo_mode=capi.HALO_CONSISTENT,
+                arithmetic=capi.ARITH_ARRAY)
+        g.init_gaussian()
+        for chunk in (1, 2, 14):
+            assert np.allclose(g.iterate(chunk), oo.iterate(chunk), rtol=REL_NORM_TOL, atol=0)
+            for r in range(nslabs):
+                assert np.array_equal(g.get("Htau", r), oo.get("Htau", r)), (nslabs, chunk, r)
+        g.close()
+    with pytest.raises(capi.B2SError):  # the array arithmetic lives in the direct kernel only
+        _mk(b2s, 64, 64, 64, kernel_variant=capi.KERNEL_TMA, arithmetic=capi.ARITH_ARRAY)
+
+
+@pytest.mark.parametrize("nslabs,halo", [(1, 0), (3, 0), (2, 1)])
+@pytest.mark.parametrize("warm", [1, 4])
+def test_new_job_through_upload_state_equals_fresh_handle(b2s, gpu, nslabs, halo, warm):
+    """A job started with upload_state / upload_state_async + commit_upload on a used handle (odd or even number of
+    earlier iterations) gives bit for bit what a fresh handle gives: the other ping-pong buffer (the reference's
+    Htau2 = @zeros) and the iteration parity are reset."""
+    import torch
+    shape = (64, 32, 20)
+    rng = np.random.default_rng(5)
+    job = [np.asfortranarray(rng.random(shape)) for _ in range(nslabs)]
+    fresh = _mk(b2s, *shape, nslabs=nslabs, devices=[0] * nslabs, halo_mode=halo)
+    fresh.set_initial(np.concatenate([j.ravel(order="F") for j in job]))
+    e_ref = fresh.iterate(7)
+    ref = [fresh.get("Htau", r) for r in range(nslabs)]
+    fresh.close()
+    for use_async in (False, True):
+        g = _mk(b2s, *shape, nslabs=nslabs, devices=[0] * nslabs, halo_mode=halo)
+        g.init_gaussian()
+        g.iterate(warm)  # leaves stale data in both buffers and (warm odd) the parity flipped
+        pins = [torch.from_numpy(j.ravel(order="F").copy()).pin_memory() for j in job]
+        for r in range(nslabs):
+            if use_async:
+                g.upload_state_async(pins[r], slab=r)
+                g.commit_upload(slab=r)
+            else:
+                g.upload_state(pins[r], slab=r)
+        e = g.iterate(7)
+        assert np.array_equal(e, e_ref), (use_async, e, e_ref)
+        for r in range(nslabs):
+            assert np.array_equal(g.get("Htau", r), ref[r]), (use_async, r)
+        g.close()
+
+
+def test_x_g_covers_the_rank_grid_and_thin_grids_are_rejected(b2s, gpu):
+    from b200stencil import capi, part1
+    X, H, _ = part1.diffusion_3D_kernel_programming(nx=20, ny=18, nz=16, ttot=0.2, tol=1e-3, verbose=False, dims=(2, 2, 1))
+    assert len(X) == H.shape[0] == 40  # LinRange(dx/2, lx-dx/2, nx*dims[1]), part1_kernel_programming.jl:221
+    # more xy tiles than block partials: an error, not a hang
+    with pytest.raises(capi.B2SError) as ei:
+        part1.Diffusion3D(4097, 4100, 3)
+    assert ei.value.code == capi.ERR_BAD_SIZE

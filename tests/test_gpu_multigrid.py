@@ -448,3 +448,23 @@ def test_full_size_properties(p2):
         lap = (x[2:, 1:-1] + x[:-2, 1:-1] + x[1:-1, 2:] + x[1:-1, :-2] - 4 * x[1:-1, 1:-1]) * (n - 1) ** 2
         res = lap - b[1:-1, 1:-1]
         assert np.sqrt(np.sum(res ** 2) / (n * n)) < 2e-6 * np.sqrt(np.sum(b ** 2) / (n * n))
+
+
+def test_navier_stokes_2049_step_vs_oracle(p2, oracle):
+    """Config #4 grid (2049^2, beta = 0.5, Pr = 0.1, tol 1e-7): one full semi-implicit step -- three MG solves with the
+    streaming level kernels, the fused Navier-Stokes kernels around them -- bit-exact against the oracle, same V-cycle
+    counts."""
+    nx = ny = 2049
+    W0 = rnd((nx, ny), 31)
+    P = oracle.NSParams(nx=nx, ny=ny, beta=0.5, Pr=0.1, tol=1e-7)
+    S, T, W = oracle.farray((nx, ny)), oracle.ns_init_cosine(nx, ny), W0.copy(order="F")
+    sim = p2.NavierStokes2D(p2.SimIn_t(nx=nx, ny=ny, beta=0.5, Pr=0.1, tol=1e-7))
+    sim.init_cosine("T")
+    sim.set_field("W", W0)
+    io, _ = oracle.ns_step(P, S, T, W)
+    ig = sim.step()
+    assert (ig.cycles_S, ig.cycles_T, ig.cycles_W) == (io.cycles_S, io.cycles_T, io.cycles_W)
+    assert ig.dt == io.dt
+    for name, ref in (("S", S), ("T", T), ("W", W)):
+        assert np.array_equal(sim.get_field(name), ref), name
+    sim.close()
