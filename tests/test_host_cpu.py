@@ -199,3 +199,160 @@ def test_bench_reference_arm_contract(tmp_path):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+# ---- the Julia boundary, checked mechanically (Julia cannot run in this image) ----------------------------------------
+_JL = os.path.join(ROOT, "finalprojectrepo.jl_b200", "julia", "B200Stencil.jl")
+_HDR = os.path.join(ROOT, "include", "b200stencil.h")
+_JL_STRUCT_OF = {"Diff3DConfig": "b2s_diff3d_config", "Diff3DParams": "b2s_diff3d_params", "MGConfig": "b2s_mg_config",
+                 "NS2DParams": "b2s_ns2d_params", "NS2DStepInfo": "b2s_ns2d_stepinfo"}
+_OPAQUE = ("b2s_diff3d", "b2s_mg", "b2s_ns2d")
+
+
+def _c_type(decl):
+    """'const double *Ht_dev' -> canonical C type without the parameter name: 'double*'."""
+    import re
+    d = re.sub(r"\bconst\b", " ", decl).strip()
+    stars = d.count("*")
+    d = d.replace("*", " ")
+    words = d.split()
+    base = words[:-1] if len(words) > 1 else words  # the last word is the parameter name (prototypes here always name them)
+    if not base:
+        base = words
+    return " ".join(base) + "*" * stars
+
+
+def _header_prototypes():
+    import re
+    txt = re.sub(r"/\*.*?\*/", " ", open(_HDR).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w \*]*?)\b(b2s_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        ret = re.sub(r"\bconst\b", " ", ret).replace(" ", "")
+        params = [] if args in ("void", "") else [_c_type(a) for a in args.split(",")]
+        protos[name] = (ret, params)
+    structs = {}
+    for m in re.finditer(r"typedef\s+struct\s*\{(.*?)\}\s*(b2s_\w+)\s*;", txt, flags=re.S):
+        fields = []
+        for stmt in m.group(1).split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            first, *rest = [p.strip() for p in stmt.split(",")]
+            t = _c_type(first)
+            fields.append(t)
+            fields.extend([t] * len(rest))  # "int nx, ny, nz;"
+        structs[m.group(2)] = fields
+    return protos, structs
+
+
+def _julia_matches_c(jl, c):
+    """Is the Julia ccall argument type `jl` a correct binding of the C parameter type `c`?"""
+    scalars = {"Cint": "int", "Cdouble": "double", "Csize_t": "size_t", "Clonglong": "long long", "Cstring": "char*"}
+    if jl in scalars:
+        return scalars[jl] == c
+    if jl in ("CuPtr{Cdouble}", "Ptr{Cdouble}", "Ref{Cdouble}"):
+        return c == "double*"
+    if jl in ("Ptr{Cint}", "Ref{Cint}"):
+        return c == "int*"
+    if jl in ("Ptr{Clonglong}", "Ref{Clonglong}"):
+        return c == "long long*"
+    if jl == "Ptr{Cvoid}":  # opaque handle or void* (stream, blob)
+        return c == "void*" or c in tuple(o + "*" for o in _OPAQUE)
+    if jl == "Ptr{UInt8}":
+        return c == "void*"
+    if jl == "Ref{Ptr{Cvoid}}":
+        return c in tuple(o + "**" for o in _OPAQUE) or c == "double**"
+    if jl.startswith("Ref{") and jl[4:-1] in _JL_STRUCT_OF:
+        return c == _JL_STRUCT_OF[jl[4:-1]] + "*"
+    return False
+
+
+def test_julia_ccall_signatures_match_header():
+    """Every ccall in julia/B200Stencil.jl names a function the header declares, with the same arity, a matching return
+    type and argument types that are correct bindings of the C parameter types; every mirrored struct has the header's
+    field sequence. (The reference's host language cannot be executed here, so the boundary is checked mechanically.)"""
+    import re
+    src = open(_JL).read()
+    protos, structs = _header_prototypes()
+    assert len(protos) >= 50
+    calls = re.findall(r"ccall\(\(:(b2s_\w+),\s*lib\),\s*(\w+),\s*\(([^()]*)\)", src, flags=re.S)
+    assert len(calls) >= 30
+    seen = set()
+    for name, ret, argt in calls:
+        assert name in protos, f"{name} is not declared in b200stencil.h"
+        cret, cparams = protos[name]
+        jl_args = [a.strip() for a in argt.replace("\n", " ").split(",") if a.strip()]
+        assert len(jl_args) == len(cparams), (name, jl_args, cparams)
+        assert _julia_matches_c(ret, cret if cret != "constchar*" else "char*"), (name, ret, cret)
+        for i, (j, c) in enumerate(zip(jl_args, cparams)):
+            assert _julia_matches_c(j, c), f"{name} argument {i + 1}: Julia {j} does not bind C `{c}`"
+        seen.add(name)
+    # the entry points of SURVEY 8(b) are all reachable from Julia
+    for need in ("b2s_diff3d_create", "b2s_diff3d_solve_timestep", "b2s_diff3d_gather", "b2s_diff3d_ipc_connect",
+                 "b2s_diffusion3d_step_tau", "b2s_mg_create", "b2s_mg_solve", "b2s_mg_vcycle", "b2s_mg_pcg_solve", "b2s_cg_solve",
+                 "b2s_iteration2d", "b2s_residual2d", "b2s_restrict_inject2d", "b2s_prolongate2d", "b2s_matvec2d",
+                 "b2s_apply_bc2d", "b2s_ns2d_create", "b2s_ns2d_step", "b2s_ns2d_get_field", "b2s_ns2d_set_field"):
+        assert need in seen, need
+    for fn in ("diffusion_3D_kernel_programming", "diffusion_3D_array_programming", "main", "MGsolve_2DPoisson!",
+               "Vcycle_2DPoisson!", "iteration_2DPoisson!", "residual_2DPoisson_wrapper!", "restrict_wrapper!",
+               "prolongate_wrapper!", "preallocate_buffers", "cg!", "matrix_free_matvec_prod_wrapper!", "navier_stokes_2D"):
+        assert re.search(r"function\s+" + re.escape(fn) + r"\(", src), fn
+    for st in ("SimIn_t", "SimOut_t", "MGOpt", "BenchResults"):
+        assert re.search(r"struct\s+" + st + r"\b", src), st
+    # struct layouts
+    jl_ct = {"Cint": "int", "Cdouble": "double", "Ptr{Cint}": "int*"}
+    for jname, cname in _JL_STRUCT_OF.items():
+        m = re.search(r"^struct\s+" + jname + r"\b(.*?)^end", src, flags=re.S | re.M)
+        assert m, jname
+        fields = [jl_ct[t] for t in re.findall(r"^\s*\w+::([\w{}]+)", m.group(1), flags=re.M)]
+        assert fields == structs[cname], (jname, fields, structs[cname])
+
+
+def test_ctypes_signatures_match_header(b2s):
+    """The same mechanical check for the Python mirror: arity and pointer/scalar kinds of every SIGNATURES entry."""
+    from b200stencil import capi
+    protos, structs = _header_prototypes()
+    for name, (res, args) in capi.SIGNATURES.items():
+        cret, cparams = protos[name]
+        assert len(args) == len(cparams), (name, len(args), cparams)
+        for a, c in zip(args, cparams):
+            if a is C.c_int:
+                assert c == "int", (name, c)
+            elif a is C.c_double:
+                assert c == "double", (name, c)
+            elif a is C.c_size_t:
+                assert c == "size_t", (name, c)
+            else:
+                assert c.endswith("*"), (name, a, c)
+    for py, cname in ((capi.Diff3DConfig, "b2s_diff3d_config"), (capi.Diff3DParams, "b2s_diff3d_params"),
+                      (capi.MGConfig, "b2s_mg_config"), (capi.NS2DParams, "b2s_ns2d_params"), (capi.NS2DStepInfo, "b2s_ns2d_stepinfo")):
+        kinds = ["int" if t is C.c_int else "double" if t is C.c_double else "int*" for _, t in py._fields_]
+        assert kinds == structs[cname], (cname, kinds, structs[cname])
+
+
+def test_experiment_csv_schemas_are_the_references(b2s, tmp_path):
+    """The header lines of benchmark-results/bench_diffusion_scaling_gpu.csv:1, bench_multigrid_gpu.csv:1 and
+    part2_semi_implicit_vs_explicit_experiment_results.csv:1 of the reference, and Julia's spelling of Bool / Float64."""
+    from b200stencil import experiments as E
+    assert ",".join(E.SCALING_COLUMNS) == ("delta_t,Work,Performance,Memory,Intensity,Throughput,use_shared_memory,use_gpu,"
+                                           "strong_scaling,n_threads,n_mpi_ranks")
+    assert ",".join(E.MULTIGRID_COLUMNS) == "execution_policy,coarse_solver,k,l,median_time,mean_time,std_time,seed,use_gpu,nthreads"
+    assert ",".join(E.SEMI_IMPLICIT_COLUMNS) == "nx,ny,Pr,beta,t_elapsed,timed_iters"
+    assert E.DIMS_DICT == {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}  # part1_scaling_experiments.jl:35-40
+    fn = str(tmp_path / "r" / "bench.csv")
+    row = dict(delta_t=49.015100955963135, Work=6.9700101156e11, Performance=1.4220128041482763e10, Memory=1.44563172768e12,
+               Intensity=0.48214285714285715, Throughput=2.949359890085314e10, use_shared_memory=True, use_gpu=True,
+               strong_scaling=True, n_threads=1, n_mpi_ranks=1)
+    E.append_row(fn, E.SCALING_COLUMNS, row)
+    E.append_row(fn, E.SCALING_COLUMNS, dict(row, use_shared_memory=False))
+    lines = open(fn).read().splitlines()
+    assert lines[0] == ",".join(E.SCALING_COLUMNS) and len(lines) == 3
+    # the reference's own first data row (bench_diffusion_scaling_gpu.csv:2), digit for digit up to Julia's e-notation
+    assert lines[1].split(",")[0] == "49.015100955963135" and lines[1].endswith(",true,true,true,1,1")
+    assert lines[2].endswith(",false,true,true,1,1")
+    import pandas as pd
+    df = pd.read_csv(fn)
+    assert df.Work[0] == 6.9700101156e11 and list(df.columns) == E.SCALING_COLUMNS
+    with pytest.raises(ValueError):
+        E.append_row(fn, E.MULTIGRID_COLUMNS, {c: 0 for c in E.MULTIGRID_COLUMNS})
