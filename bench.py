@@ -333,6 +333,12 @@ def main():
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches1, _ = s.stats()
+    per_rank_ms = [dev_ms / args.steps]
+    if dist is not None:  # every rank's own device time: tells a slow GPU from a synchronisation cost
+        t = torch.zeros(N, dtype=torch.float64, device=f"cuda:{dev}")
+        t[rank] = dev_ms / args.steps
+        dist.all_reduce(t)
+        per_rank_ms = [float(v) for v in t.tolist()]
     dev_ms = max_over_ranks(dev_ms)
     wall = max_over_ranks(wall)
     value = BYTES_PER_CELL * cells * iters * args.steps * N / (dev_ms * 1e-3) / 1e9
@@ -343,7 +349,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "step_tma_kernel (fused flux/residual/update + norm + exit test)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells,
-                "avg_launch_ms": kern_ms}
+                "avg_launch_ms": kern_ms, "per_rank_ms_per_step": per_rank_ms}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:

@@ -41,10 +41,38 @@ constexpr int kSlotGens = 4;
 // Four generations (seq mod 4): with the lagged evaluation of z-slab stacks a rank publishes partial s+4 only after every
 // rank has finished kernel s+2, i.e. after partial s has been consumed everywhere (two generations suffice for the
 // per-iteration handshake of general decompositions).
+// A partial travels as two self-validating 8-byte words (value bits 31..0 | seq32 << 32, value bits 63..32 | seq32 << 32):
+// naturally aligned 8-byte stores are single transactions, so the sender needs NO fence and no separate flag store (a
+// release per destination used to cost one NVLink round trip each, in the tail of every step kernel) and the receiver
+// polls until both words carry the sequence number it waits for.
 struct RankSlots {
-    double value[kSlotGens][kMaxRanks];
-    unsigned long long seq[kSlotGens][kMaxRanks];
+    unsigned long long w[kSlotGens][kMaxRanks][2];
 };
+
+__device__ __forceinline__ void slot_publish(RankSlots *dst, int gen, int rank, double value, unsigned long long seq)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    st_relaxed_sys_u64(&dst->w[gen][rank][0], (bits & 0xffffffffull) | tag);
+    st_relaxed_sys_u64(&dst->w[gen][rank][1], (bits >> 32) | tag);
+}
+// false on timeout
+__device__ __forceinline__ bool slot_consume(const RankSlots *mine, int gen, int rank, unsigned long long seq, long long timeout,
+                                             double *value)
+{
+    const unsigned long long tag = seq & 0xffffffffull;
+    const long long t0 = clock64();
+    for (;;) {
+        const unsigned long long a = ld_relaxed_sys_u64(&mine->w[gen][rank][0]);
+        const unsigned long long b = ld_relaxed_sys_u64(&mine->w[gen][rank][1]);
+        if ((a >> 32) == tag && (b >> 32) == tag) {
+            *value = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+            return true;
+        }
+        if (clock64() - t0 > timeout) return false;
+        __nanosleep(32);
+    }
+}
 
 // z-slab stacks: per-tile halo flags in every rank's arena, written by the two z neighbours (peer stores), read locally.
 // A flag holds the sequence number of the neighbour's step kernel that set it (monotonic, never reset).
@@ -207,9 +235,7 @@ __device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, d
         if (p.peer_slots != nullptr) {
             const unsigned long long sq = p.flagged ? seq : p.state->seq;
             const int g = (int)(sq & (unsigned long long)(kSlotGens - 1));
-            for (int r = 0; r < p.nranks; ++r) p.peer_slots[r]->value[g][p.myrank] = total;
-            __threadfence_system();
-            for (int r = 0; r < p.nranks; ++r) st_release_sys_u64(&p.peer_slots[r]->seq[g][p.myrank], sq);
+            for (int r = 0; r < p.nranks; ++r) slot_publish(p.peer_slots[r], g, p.myrank, total, sq);
         } else if (p.fuse_finalize) {
             pt_finalize(p.state, total, p.err_hist);
         }
@@ -226,14 +252,9 @@ __device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, d
         const unsigned long long want = seq - 1;
         const int g1 = (int)(want & (unsigned long long)(kSlotGens - 1));
         if (tid < p.nranks) {
-            const long long t0 = clock64();
-            bool ok = true;
-            while (ld_acquire_sys_u64(&p.my_slots->seq[g1][tid]) != want) {
-                if (clock64() - t0 > p.timeout_cycles) { ok = false; break; }
-                __nanosleep(32);
-            }
-            if (!ok) failed = 1;
-            vals[tid] = ld_relaxed_sys_f64(&p.my_slots->value[g1][tid]);
+            double v = 0.0;
+            if (!slot_consume(p.my_slots, g1, tid, want, p.timeout_cycles, &v)) failed = 1;
+            vals[tid] = v;
         }
         __syncthreads();
     }
@@ -538,14 +559,9 @@ __global__ void pt_finalize_kernel(PTState *state, double *err_hist, const doubl
         const unsigned long long seq = lagged ? state->seq - 1 : state->seq;
         const int g = (int)(seq & (unsigned long long)(kSlotGens - 1));
         if (t < nranks) {
-            const long long t0 = clock64();
-            bool ok = true;
-            while (ld_acquire_sys_u64(&slots->seq[g][t]) != seq) {
-                if (clock64() - t0 > timeout_cycles) { ok = false; break; }
-                __nanosleep(64);
-            }
-            if (!ok) failed = 1;
-            vals[t] = ld_relaxed_sys_f64(&slots->value[g][t]);
+            double v = 0.0;
+            if (!slot_consume(slots, g, t, seq, timeout_cycles, &v)) failed = 1;
+            vals[t] = v;
         }
     } else if (t < nranks) {
         vals[t] = local[t];

@@ -48,6 +48,11 @@ struct b2s_mg {
     double *u[kMaxLevels] = {}, *rhs[kMaxLevels] = {}, *tmp[kMaxLevels] = {};  // u/rhs for l >= 1, tmp for all
     int first_smem = 0;  // first level handled by the collapsed kernel
     size_t coarse_smem = 0;
+    // thread-block-cluster kernel for the latency-bound middle levels (variant A, fused): levels mid_first .. first_smem-1
+    // live in the distributed shared memory of one cluster of mid_nc blocks, first_smem.. in block 0 (mg_mid_cluster_kernel)
+    int mid_first = 0;   // == first_smem: disabled
+    int mid_nc = 0, mid_base = 0;
+    size_t mid_smem = 0;
     MGCall *call_dev = nullptr, *call_pin = nullptr;  // call_pin: upload staging [MGCall][LevelCoef...], then the read-back MGCall
     double *hist_dev = nullptr, *hist_pin = nullptr;
     double *sumsq_dev = nullptr;  // [0] last sweep, [1] f, [2],[3] rbgs colours
@@ -236,11 +241,12 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
             }
         }
     };
-    const int fs = h->coarse_global ? h->nlev - 1 : h->first_smem;
+    const bool use_mid = !h->coarse_global && h->mid_nc > 0 && h->mid_first < h->first_smem;
+    const int fs = h->coarse_global ? h->nlev - 1 : (use_mid ? h->mid_first : h->first_smem);
     const bool fused_b = fused_variant_b(c);
     const bool fused = fused_variant_a(c) || fused_b;
     // the finest level's fused upward kernel finishes the cycle itself (norm -> r_rms -> exit test) when there is one
-    const bool end_fused = fused && (h->coarse_global ? h->nlev - 1 : h->first_smem) > 0;
+    const bool end_fused = fused && fs > 0;
     auto tile_args = [&](int l) {
         TileArgs t = {};
         t.cp = cp; t.level = l; t.rhs = h->rhs[l]; t.nx = h->nx[l]; t.ny = h->ny[l]; t.nxc = h->nx[l + 1]; t.nyc = h->ny[l + 1];
@@ -355,6 +361,27 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
         long long nn = 0;
         B2S_CHECK(coarse_global_solve(h, st, &nn));
         n += nn;
+    } else if (use_mid) {
+        // middle levels in the distributed shared memory of one thread-block cluster + the collapsed tail in its block 0
+        MidArgs m = {};
+        const int f2 = h->first_smem;
+        m.ser.cp = cp; m.ser.level0 = f2; m.ser.nlev = h->nlev - f2;
+        for (int l = f2; l < h->nlev; ++l) { m.ser.nx[l - f2] = h->nx[l]; m.ser.ny[l - f2] = h->ny[l]; }
+        m.ser.coarse_solve_size = c.coarse_solve_size; m.ser.coarse_solver = c.coarse_solver;
+        m.ser.smoother = c.smoother; m.ser.restriction = c.restriction;
+        m.ser.prof = h->prof_dev;
+        m.level0 = fs; m.ndist = f2 - fs; m.base = h->mid_base;
+        for (int l = fs; l < f2; ++l) { m.nx[l - fs] = h->nx[l]; m.ny[l - fs] = h->ny[l]; }
+        m.rhs_in = h->rhs[fs]; m.u_out = h->u[fs];
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(h->mid_nc, 1, 1); lc.blockDim = dim3(kMidThreads, 1, 1);
+        lc.dynamicSmemBytes = h->mid_smem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = h->mid_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        B2S_CUDA(cudaLaunchKernelEx(&lc, mg_mid_cluster_kernel, m));
+        ++n;
     } else
     // collapsed coarse hierarchy
     {
@@ -715,6 +742,7 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
         }
         h->first_smem = fs;
         h->coarse_smem = bytes;
+        h->mid_first = fs;
     }
     DeviceGuard guard;
     guard.set(cfg->device);
@@ -762,6 +790,48 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
     MG_CUDA(cudaMalloc(&h->ticket, 64));
     MG_CUDA(cudaMemset(h->ticket, 0, 64));
     MG_CUDA(cudaFuncSetAttribute(mg_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemLimit + 1024));
+    // cluster kernel for the middle levels: the largest cluster (16 blocks: non-portable size, 8: portable) whose blocks can
+    // hold their bands; the finest distributed level is the largest one that still fits (never level 0: its arrays are the
+    // caller's and its upward kernel finishes the cycle). B2S_MG_CLUSTER = 0 disables, 8 / 16 pins the cluster size.
+    if (fused_variant_a(*cfg) && !h->coarse_global && h->first_smem >= 2) {
+        const char *ec = getenv("B2S_MG_CLUSTER");
+        const int want = (ec && *ec) ? atoi(ec) : 0;  // TODO(measured slower than the per-level kernels so far): off by default
+        const int last = h->first_smem - 1;
+        const size_t limit = 200 * 1024;  // + 24 KB of static shared memory (the in-warp coarsest solver's batches) <= 227 KB
+        const int tries[2] = {16, 8};
+        for (int t_ = 0; t_ < 2 && want != 0 && h->mid_nc == 0; ++t_) {
+            const int NC = tries[t_];
+            if (want > 0 && want != NC) continue;
+            if ((h->ny[last] - 1) % NC != 0 || (h->ny[last] - 1) / NC < 2) continue;
+            MidArgs m = {};
+            m.base = (h->ny[last] - 1) / NC;
+            int top = -1;
+            for (int cand = last; cand >= 1 && last - cand + 1 <= kMidMaxDist; --cand) {
+                m.ndist = last - cand + 1;
+                for (int l = cand; l <= last; ++l) { m.nx[l - cand] = h->nx[l]; m.ny[l - cand] = h->ny[l]; }
+                if (mid_dist_doubles(m) * sizeof(double) + h->coarse_smem > limit) break;
+                top = cand;
+            }
+            if (top < 0) continue;
+            m.ndist = last - top + 1;
+            for (int l = top; l <= last; ++l) { m.nx[l - top] = h->nx[l]; m.ny[l - top] = h->ny[l]; }
+            const size_t smem = mid_dist_doubles(m) * sizeof(double) + h->coarse_smem;
+            MG_CUDA(cudaFuncSetAttribute(mg_mid_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+            if (NC > 8) MG_CUDA(cudaFuncSetAttribute(mg_mid_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(NC, 1, 1); lc.blockDim = dim3(kMidThreads, 1, 1); lc.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, mg_mid_cluster_kernel, &lc) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            h->mid_nc = NC; h->mid_base = m.base; h->mid_first = top; h->mid_smem = smem;
+        }
+    }
     {
         const char *e = getenv("B2S_MG_TILE");
         h->tile_choice = (e && *e) ? atoi(e) : -1;  // -1: per level (tile_choice_for)

@@ -14,6 +14,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace b2s {
 
 constexpr int kMaxLevels = 24;
@@ -2177,48 +2179,23 @@ __device__ __forceinline__ double sm_coarsest(const G &g, double *u, const doubl
     return ss;
 }
 
-__global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
+// The chain of one thread block over levels that live in ITS shared memory: downward leg, coarsest solve, upward leg
+// (multigrid.jl:121-167 for every level of the block). U[0] and F[0] hold the unknown and the right-hand side of the first
+// level on entry; U[0] holds the result on exit. Returns the sum of res^2 of the last sweep of the first level when
+// `top_norm` (valid on every thread). All threads of the block must call.
+__device__ __forceinline__ double coarse_chain(const CoarseArgs &a, double *const *U, double *const *F, double *const *T,
+                                               const LevelCoef *slev, double *red, double c, double tol, int apply_bcs,
+                                               bool top_norm)
 {
-    extern __shared__ double sm[];
-    __shared__ double red[32];
     const MGCall *cp = a.cp;
-    if (cp->done) return;
-    const double c = cp->c, tol = cp->tol;
-    const int apply_bcs = cp->apply_bcs;
     const bool fw = a.restriction == B2S_RESTRICT_FW;
     BlockGroup bg{red};
-    // carve shared memory: per level u, rhs, tmp; then CG scratch for the coarsest
-    double *U[kMaxLevels], *F[kMaxLevels], *T[kMaxLevels];
-    {
-        double *ptr = sm;
-        for (int l = 0; l < a.nlev; ++l) {
-            const int n = a.nx[l] * a.ny[l];
-            U[l] = ptr; ptr += n;
-            F[l] = ptr; ptr += n;
-            T[l] = ptr; ptr += n;
-        }
-        U[a.nlev] = ptr;  // CG scratch (4 * n_coarsest)
-    }
-    const double *rhs_g = a.rhs_in != nullptr ? a.rhs_in : cp->rhs;
-    double *u_g = a.u_io != nullptr ? a.u_io : cp->u;
-    __shared__ LevelCoef slev[kMaxLevels];  // per-level constants of this call (host-computed), fetched once up front
-    {
-        if (threadIdx.x < a.nlev) slev[threadIdx.x] = *level_consts(cp, a.level0 + threadIdx.x);
-        const int n = a.nx[0] * a.ny[0];
-        for (int p = threadIdx.x; p < n; p += blockDim.x) {
-            F[0][p] = rhs_g[p];
-            U[0][p] = a.u_is_input ? u_g[p] : 0.0;
-        }
-        __syncthreads();
-    }
     auto coef_of = [&](int l) {
         Coef k;
         k.C = slev[l].C; k._h2 = slev[l]._h2; k.w = slev[l].wJ;
         return k;
     };
     double last_ss = 0.0;
-    if (a.prof != nullptr && threadIdx.x == 0) a.prof[0] = 0;
-    coarse_stamp(a);
     // ---- downward leg ---------------------------------------------------------------------------------------
     for (int l = 0; l + 1 < a.nlev; ++l) {
         const int nx = a.nx[l], ny = a.ny[l], nxc = a.nx[l + 1], nyc = a.ny[l + 1];
@@ -2269,7 +2246,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
         for (Idx2 q(threadIdx.x, blockDim.x, nx); q.p < nx * ny; q.next())
             U[l][q.p] = U[l][q.p] - prolong_value_bc(U[l + 1], nxc, nyc, nx, q.i, q.j, apply_bcs);
         __syncthreads();
-        const bool top = (l == 0 && a.sumsq_out != nullptr);
+        const bool top = (l == 0 && top_norm);
         if (a.smoother == B2S_SMOOTH_RBGS) {
             sm_rbgs(bg, U[l], F[l], nx, ny, h, c, false);
             last_ss = sm_rbgs(bg, U[l], F[l], nx, ny, h, c, top);
@@ -2279,6 +2256,44 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
         }
         coarse_stamp(a);
     }
+    return last_ss;
+}
+
+__global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
+{
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    const MGCall *cp = a.cp;
+    if (cp->done) return;
+    const double c = cp->c, tol = cp->tol;
+    const int apply_bcs = cp->apply_bcs;
+    // carve shared memory: per level u, rhs, tmp; then CG scratch for the coarsest
+    double *U[kMaxLevels], *F[kMaxLevels], *T[kMaxLevels];
+    {
+        double *ptr = sm;
+        for (int l = 0; l < a.nlev; ++l) {
+            const int n = a.nx[l] * a.ny[l];
+            U[l] = ptr; ptr += n;
+            F[l] = ptr; ptr += n;
+            T[l] = ptr; ptr += n;
+        }
+        U[a.nlev] = ptr;  // CG scratch (4 * n_coarsest)
+    }
+    const double *rhs_g = a.rhs_in != nullptr ? a.rhs_in : cp->rhs;
+    double *u_g = a.u_io != nullptr ? a.u_io : cp->u;
+    __shared__ LevelCoef slev[kMaxLevels];  // per-level constants of this call (host-computed), fetched once up front
+    {
+        if (threadIdx.x < a.nlev) slev[threadIdx.x] = *level_consts(cp, a.level0 + threadIdx.x);
+        const int n = a.nx[0] * a.ny[0];
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            F[0][p] = rhs_g[p];
+            U[0][p] = a.u_is_input ? u_g[p] : 0.0;
+        }
+        __syncthreads();
+    }
+    if (a.prof != nullptr && threadIdx.x == 0) a.prof[0] = 0;
+    coarse_stamp(a);
+    const double last_ss = coarse_chain(a, U, F, T, slev, red, c, tol, apply_bcs, a.sumsq_out != nullptr);
     {
         const int n = a.nx[0] * a.ny[0];
         for (int p = threadIdx.x; p < n; p += blockDim.x) u_g[p] = U[0][p];
@@ -2286,6 +2301,208 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
     }
     __syncthreads();
     coarse_stamp(a);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Thread-block-cluster kernel for the latency-bound middle of the V-cycle (variant A: damped Jacobi + injection).
+// Levels of ~1e3 .. 7e4 points (33^2 .. 257^2 at the 1025^2 bench shape) are chains of dependent sweeps that no amount of
+// SMs speeds up: as separate kernels each level costs two dependent launches (~4 us each, 8 launches = 40 % of the
+// cycle). Here ONE cluster of NC thread blocks keeps those levels in DISTRIBUTED SHARED MEMORY -- every block owns a
+// band of rows of every such level (u, tmp with one halo row on each side, rhs) -- and walks down and up the hierarchy
+// with a cluster barrier (barrier.cluster, ~0.2 us) where a kernel boundary (>= 1.4 us plus the refill of every block's
+// pipeline) used to be. Halo rows are PUSHED: the thread that computes a point of a band's first / last row also stores
+// it into the neighbour block's halo row through the cluster's shared-memory window (st.shared::cluster, no read
+// latency on the critical path); the barrier publishes them. The levels below (<= 17^2) are the one-block chain of
+// mg_coarse_kernel, run by block 0 of the cluster on data the other blocks restricted into its shared memory.
+// Every point is produced by the arithmetic of the unfused kernels: bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMidThreads = 512;
+constexpr int kMidMaxDist = 6;
+struct MidArgs {
+    CoarseArgs ser;             // the serial tail run by block 0 (ser.level0 = global index of its first level)
+    int level0;                 // global index of the first (finest) distributed level
+    int ndist;                  // distributed levels
+    int nx[kMidMaxDist], ny[kMidMaxDist];
+    int base;                   // rows per block on the LAST distributed level: ny[ndist-1] - 1 == NC * base
+    const double *rhs_in;       // global rhs of level0 (written by the fused downward kernel of the level above)
+    double *u_out;              // global unknown of level0 (read by the fused upward kernel of the level above)
+};
+
+// shared-memory doubles per block of the distributed levels (every block uses the same offsets)
+__host__ __device__ inline size_t mid_dist_doubles(const MidArgs &m)
+{
+    size_t n = 0;
+    for (int d = 0; d < m.ndist; ++d) {
+        const size_t rows = ((size_t)m.base << (m.ndist - 1 - d)) + 1;
+        n += (2 * (rows + 2) + rows) * (size_t)m.nx[d];
+    }
+    return n;
+}
+
+// one damped-Jacobi sweep over this block's band [r0, r1) of a level: src/dst have a halo row on each side (local row
+// lr = j - r0 + 1), F has the band only. Points of the first / last band row are also stored into the neighbour's halo
+// row (rem_lo: the lower neighbour's halo row above ITS band; rem_hi: the upper neighbour's halo row 0); nullptr at the ends.
+__device__ __forceinline__ void mid_sweep(const double *__restrict__ src, const double *__restrict__ F, double *__restrict__ dst,
+                                          int nx, int ny, int r0, int r1, const Coef &k, double *rem_lo, double *rem_hi)
+{
+    const int rows = r1 - r0, n = rows * nx;
+    for (Idx2 q(threadIdx.x, kMidThreads, nx); q.p < n; q.next()) {
+        const int i = q.i, lr = q.j, j = r0 + lr;
+        const int s = (lr + 1) * nx + i;
+        double v = src[s];
+        if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
+            const double r = ((src[s + 1] + src[s - 1] + src[s + nx] + src[s - nx] - k.C * v) * k._h2 - F[q.p]);
+            v = v + k.w * r;
+        }
+        dst[s] = v;
+        if (lr == 0 && rem_lo != nullptr) rem_lo[i] = v;
+        if (lr == rows - 1 && rem_hi != nullptr) rem_hi[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kMidThreads) mg_mid_cluster_kernel(const MidArgs m)
+{
+    namespace cgr = cooperative_groups;
+    cgr::cluster_group cluster = cgr::this_cluster();
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ LevelCoef slev[kMaxLevels];
+    const MGCall *cp = m.ser.cp;
+    if (cp->done) return;  // the same value in every block of the cluster: nobody is left waiting at a barrier
+    const int NC = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const double c = cp->c, tol = cp->tol;
+    const int apply_bcs = cp->apply_bcs;
+    const int nd = m.ndist;
+    // ---- carve-up (identical offsets in every block) ----------------------------------------------------------
+    double *Ud[kMidMaxDist], *Td[kMidMaxDist], *Fd[kMidMaxDist];
+    int r0[kMidMaxDist], r1[kMidMaxDist], rowsmax[kMidMaxDist];
+    double *ptr = sm;
+    for (int d = 0; d < nd; ++d) {
+        const int per = m.base << (nd - 1 - d);
+        rowsmax[d] = per + 1;
+        r0[d] = rank * per;
+        r1[d] = rank == NC - 1 ? m.ny[d] : (rank + 1) * per;
+        Ud[d] = ptr; ptr += (size_t)(rowsmax[d] + 2) * m.nx[d];
+        Td[d] = ptr; ptr += (size_t)(rowsmax[d] + 2) * m.nx[d];
+        Fd[d] = ptr; ptr += (size_t)rowsmax[d] * m.nx[d];
+    }
+    double *U[kMaxLevels], *F[kMaxLevels], *T[kMaxLevels];
+    for (int l = 0; l < m.ser.nlev; ++l) {
+        const int n = m.ser.nx[l] * m.ser.ny[l];
+        U[l] = ptr; ptr += n;
+        F[l] = ptr; ptr += n;
+        T[l] = ptr; ptr += n;
+    }
+    U[m.ser.nlev] = ptr;  // CG scratch of the coarsest level
+    // ---- load: constants, rhs band of the first level, u = 0 ------------------------------------------------------
+    if ((int)threadIdx.x < nd + m.ser.nlev) slev[threadIdx.x] = *level_consts(cp, m.level0 + threadIdx.x);
+    {
+        const int nx = m.nx[0], rows = r1[0] - r0[0];
+        const double *g = m.rhs_in + (size_t)nx * r0[0];
+        for (int p = threadIdx.x; p < rows * nx; p += kMidThreads) Fd[0][p] = g[p];
+        for (int p = threadIdx.x; p < (rows + 2) * nx; p += kMidThreads) Ud[0][p] = 0.0;
+        if (rank == 0) {
+            const int n = m.ser.nx[0] * m.ser.ny[0];
+            for (int p = threadIdx.x; p < n; p += kMidThreads) U[0][p] = 0.0;
+        }
+    }
+    cluster.sync();  // also: every block of the cluster is running before anyone stores into its shared memory
+    if (rank == 0) {
+        if (m.ser.prof != nullptr && threadIdx.x == 0) m.ser.prof[0] = 0;
+        coarse_stamp(m.ser);
+    }
+    auto coef_of = [&](int l) {
+        Coef k;
+        k.C = slev[l].C; k._h2 = slev[l]._h2; k.w = slev[l].wJ;
+        return k;
+    };
+    // neighbour halo rows of array `a` (one of Ud/Td) of level d
+    auto rem_lo_of = [&](double *a, int d) -> double * {
+        if (rank == 0) return nullptr;
+        const int per = m.base << (nd - 1 - d);  // the lower neighbour is never the last block: its band has `per` rows
+        return cluster.map_shared_rank(a, rank - 1) + (size_t)(per + 1) * m.nx[d];
+    };
+    auto rem_hi_of = [&](double *a, int d) -> double * {
+        if (rank == NC - 1) return nullptr;
+        return cluster.map_shared_rank(a, rank + 1);
+    };
+    auto two_sweeps = [&](int d) {
+        const Coef k = coef_of(d);
+        mid_sweep(Ud[d], Fd[d], Td[d], m.nx[d], m.ny[d], r0[d], r1[d], k, rem_lo_of(Td[d], d), rem_hi_of(Td[d], d));
+        if (rank == 0) coarse_stamp(m.ser);
+        cluster.sync();
+        if (rank == 0) coarse_stamp(m.ser);
+        mid_sweep(Td[d], Fd[d], Ud[d], m.nx[d], m.ny[d], r0[d], r1[d], k, rem_lo_of(Ud[d], d), rem_hi_of(Ud[d], d));
+        if (rank == 0) coarse_stamp(m.ser);
+        cluster.sync();
+        if (rank == 0) coarse_stamp(m.ser);
+    };
+    // injected residual of the smoothed u at coarse point (I, J) of level d+1, from this block's band of level d
+    auto coarse_rhs = [&](int d, int I, int J, int nxc, int nyc, const Coef &k) -> double {
+        if (apply_bcs) {
+            if (I == 0) I = 1;
+            else if (I == nxc - 1) I = nxc - 2;
+        }
+        if (I < 1 || I > nxc - 2 || J < 1 || J > nyc - 2) return 0.0;
+        const int nx = m.nx[d];
+        const int s = (2 * J - r0[d] + 1) * nx + 2 * I;
+        const double *u = Ud[d];
+        return ((u[s + 1] + u[s - 1] + u[s + nx] + u[s - nx] - k.C * u[s]) * k._h2 - Fd[d][(2 * J - r0[d]) * nx + 2 * I]);
+    };
+    // ---- downward leg over the distributed levels -----------------------------------------------------------------
+    for (int d = 0; d < nd; ++d) {
+        two_sweeps(d);
+        const Coef k = coef_of(d);
+        if (d + 1 < nd) {
+            const int nxc = m.nx[d + 1], nyc = m.ny[d + 1], c0 = r0[d + 1], rowsc = r1[d + 1] - r0[d + 1];
+            for (Idx2 q(threadIdx.x, kMidThreads, nxc); q.p < rowsc * nxc; q.next())
+                Fd[d + 1][q.p] = coarse_rhs(d, q.i, c0 + q.j, nxc, nyc, k);
+            for (int p = threadIdx.x; p < (rowsc + 2) * nxc; p += kMidThreads) Ud[d + 1][p] = 0.0;
+            __syncthreads();
+            if (rank == 0) coarse_stamp(m.ser);
+        } else {  // into block 0's copy of the first serial level
+            const int nxc = m.ser.nx[0], nyc = m.ser.ny[0];
+            const int c0 = r0[d] >> 1, c1 = rank == NC - 1 ? nyc : (r1[d] >> 1);
+            double *F0 = cluster.map_shared_rank(F[0], 0);
+            for (Idx2 q(threadIdx.x, kMidThreads, nxc); q.p < (c1 - c0) * nxc; q.next())
+                F0[(c0 + q.j) * nxc + q.i] = coarse_rhs(d, q.i, c0 + q.j, nxc, nyc, k);
+            cluster.sync();
+        }
+    }
+    // ---- the serial tail in block 0 ------------------------------------------------------------------------------------
+    if (rank == 0) coarse_stamp(m.ser);
+    if (rank == 0) coarse_chain(m.ser, U, F, T, slev + nd, red, c, tol, apply_bcs, false);
+    cluster.sync();
+    if (rank == 0) coarse_stamp(m.ser);
+    // ---- upward leg ------------------------------------------------------------------------------------------------------
+    for (int d = nd - 1; d >= 0; --d) {
+        const int nx = m.nx[d], ny = m.ny[d];
+        int nxc, nyc;
+        const double *ecb;  // coarse correction, indexable with GLOBAL coarse rows
+        if (d + 1 < nd) {
+            nxc = m.nx[d + 1]; nyc = m.ny[d + 1];
+            ecb = Ud[d + 1] - (ptrdiff_t)(r0[d + 1] - 1) * nxc;
+        } else {
+            nxc = m.ser.nx[0]; nyc = m.ser.ny[0];
+            ecb = cluster.map_shared_rank(U[0], 0);
+        }
+        // u -= P(e) on the band and on its two halo rows (their coarse neighbours are in the coarse band's halo rows)
+        const int jlo = rank == 0 ? r0[d] : r0[d] - 1, jhi = rank == NC - 1 ? r1[d] : r1[d] + 1;
+        for (Idx2 q(threadIdx.x, kMidThreads, nx); q.p < (jhi - jlo) * nx; q.next()) {
+            const int j = jlo + q.j;
+            const int s = (j - r0[d] + 1) * nx + q.i;
+            Ud[d][s] = Ud[d][s] - prolong_value_bc(ecb, nxc, nyc, nx, q.i, j, apply_bcs);
+        }
+        __syncthreads();
+        if (rank == 0) coarse_stamp(m.ser);
+        two_sweeps(d);
+    }
+    {
+        const int nx = m.nx[0], rows = r1[0] - r0[0];
+        double *g = m.u_out + (size_t)nx * r0[0];
+        const double *u = Ud[0] + nx;
+        for (int p = threadIdx.x; p < rows * nx; p += kMidThreads) g[p] = u[p];
+    }
 }
 
 // tol_rhs = tol * sqrt(sum(rhs.^2)/(nx*ny)) and the exit threshold of a global-memory coarsest Jacobi solve
