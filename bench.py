@@ -234,6 +234,12 @@ def mg_bench(device, peak):
         out["navier_stokes_2049"] = part2.bench_navier_stokes(device=device)
     except Exception as e:  # pragma: no cover
         out["navier_stokes_2049"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    try:  # BASELINE configs[3] as worded: MG-preconditioned CG for the two Dirichlet solves (full-weighting cycle)
+        from b200stencil import capi as _capi
+        out["navier_stokes_2049_mg_pcg"] = part2.bench_navier_stokes(device=device, solver=_capi.NS_SOLVER_MG_PCG,
+                                                                     mgopt=part2.MGOpt(restriction=1))
+    except Exception as e:  # pragma: no cover
+        out["navier_stokes_2049_mg_pcg"] = {"unavailable": f"{type(e).__name__}: {e}"}
     try:
         out["cpu_baseline_1025"] = mg_cpu_baseline(1025)
     except Exception as e:  # pragma: no cover

@@ -21,6 +21,8 @@ COARSE_JACOBI, COARSE_CG = 0, 1
 SMOOTH_JACOBI, SMOOTH_RBGS = 0, 1
 RESTRICT_INJECT, RESTRICT_FW = 0, 1
 POLICY_SERIAL, POLICY_PARALLEL, POLICY_PARALLEL_SHMEM = 0, 1, 2
+PCG_TOL_INITIAL_RESIDUAL, PCG_TOL_RHS = 0, 1
+NS_SOLVER_VCYCLE, NS_SOLVER_MG_PCG = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -114,11 +116,13 @@ SIGNATURES = {
     "b2s_mg_vcycle": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _dp]),
     "b2s_mg_cycles": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _i, _dp, _dp]),
     "b2s_mg_pcg_solve": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _dp, _ip]),
+    "b2s_mg_pcg_solve2": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _i, _dp, _ip]),
     "b2s_mg_last_coarse_sweeps": (_i, [_vp, _ip]),
     "b2s_mg_stats": (_i, [_vp, _llp, _dp]),
     "b2s_cg_solve": (_i, [_vp, _vp, _d, _d, _d, _d, _i, _i, _i, _i, _dp, _ip, _vp]),
     "b2s_ns2d_create": (_i, [C.POINTER(_vp), C.POINTER(NS2DParams), C.POINTER(MGConfig)]),
     "b2s_ns2d_destroy": (_i, [_vp]),
+    "b2s_ns2d_set_solver": (_i, [_vp, _i]),
     "b2s_ns2d_set_field": (_i, [_vp, _i, _vp]),
     "b2s_ns2d_get_field": (_i, [_vp, _i, _vp]),
     "b2s_ns2d_init_cosine": (_i, [_vp, _i]),

@@ -980,7 +980,14 @@ int b2s_mg_cycles(b2s_mg *h, double *u, const double *f, double hgrid, double c,
 int b2s_mg_pcg_solve(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int maxit, double *r_rms_out,
                      int *iters_out)
 {
+    return b2s_mg_pcg_solve2(h, u, f, hgrid, c, tol, maxit, B2S_PCG_TOL_INITIAL_RESIDUAL, r_rms_out, iters_out);
+}
+
+int b2s_mg_pcg_solve2(b2s_mg *h, double *u, const double *f, double hgrid, double c, double tol, int maxit, int tol_mode,
+                      double *r_rms_out, int *iters_out)
+{
     B2S_REQUIRE(h && u && f && maxit >= 0, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_REQUIRE(tol_mode == B2S_PCG_TOL_INITIAL_RESIDUAL || tol_mode == B2S_PCG_TOL_RHS, B2S_ERR_BAD_ARG, "bad tol_mode");
     B2S_REQUIRE(h->cfg.restriction == B2S_RESTRICT_FW, B2S_ERR_BAD_ARG,
                 "MG-preconditioned CG needs a symmetric V-cycle: use restriction = B2S_RESTRICT_FW");
     DeviceGuard guard;
@@ -1001,7 +1008,13 @@ int b2s_mg_pcg_solve(b2s_mg *h, double *u, const double *f, double hgrid, double
     B2S_CHECK(b2s_sumsq(r, n, &ss, st));
     h->kernel_launches += 3;
     double r_rms = sqrt(ss / N);
-    const double tolf = tol * r_rms;
+    double tolf = tol * r_rms;
+    if (tol_mode == B2S_PCG_TOL_RHS) {  // MGsolve's criterion: r_rms < tol * f_rms, f_rms over all entries (multigrid.jl:53,70-75)
+        double sf = 0.0;
+        B2S_CHECK(b2s_sumsq(f, n, &sf, st));
+        h->kernel_launches += 1;
+        tolf = tol * sqrt(sf / N);
+    }
     int it = 0;
     double rz = 0.0;
     for (int k = 1; k <= maxit && r_rms >= tolf && r_rms > 0.0; ++k) {

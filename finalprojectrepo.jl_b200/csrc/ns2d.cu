@@ -110,6 +110,7 @@ struct b2s_ns2d {
     b2s_ns2d_params p;
     b2s_mg *mg = nullptr;
     int device = 0;
+    int solver = B2S_NS_SOLVER_VCYCLE;
     double *T = nullptr, *W = nullptr, *S = nullptr, *vx = nullptr, *vy = nullptr, *Ra_dTdx = nullptr, *dT2 = nullptr,
            *dW2 = nullptr, *bufA = nullptr, *bufB = nullptr, *maxima = nullptr, *maxima_pin = nullptr;
 };
@@ -162,6 +163,14 @@ int b2s_ns2d_create(b2s_ns2d **out, const b2s_ns2d_params *p, const b2s_mg_confi
         return B2S_ERR_CUDA;
     }
     *out = h;
+    return B2S_OK;
+}
+
+int b2s_ns2d_set_solver(b2s_ns2d *h, int solver)
+{
+    B2S_REQUIRE(h, B2S_ERR_BAD_ARG, "NULL handle");
+    B2S_REQUIRE(solver == B2S_NS_SOLVER_VCYCLE || solver == B2S_NS_SOLVER_MG_PCG, B2S_ERR_BAD_ARG, "unknown solver %d", solver);
+    h->solver = solver;
     return B2S_OK;
 }
 
@@ -224,7 +233,9 @@ int b2s_ns2d_step(b2s_ns2d *h, b2s_ns2d_stepinfo *info)
     cudaStream_t st = b2s_mg_stream_internal(h->mg);
     b2s_ns2d_stepinfo inf = {};
     // D S = W, Dirichlet 0                                                               part2.jl:187
-    B2S_CHECK(b2s_mg_solve(h->mg, h->S, h->W, hh, 0.0, P.tol, P.niters, 0, &inf.r_S, &inf.cycles_S, nullptr));
+    const bool pcg = h->solver == B2S_NS_SOLVER_MG_PCG;  // S and W: Dirichlet solves; T (BCs inside the cycle) always cycles
+    if (pcg) B2S_CHECK(b2s_mg_pcg_solve2(h->mg, h->S, h->W, hh, 0.0, P.tol, P.niters, B2S_PCG_TOL_RHS, &inf.r_S, &inf.cycles_S));
+    else B2S_CHECK(b2s_mg_solve(h->mg, h->S, h->W, hh, 0.0, P.tol, P.niters, 0, &inf.r_S, &inf.cycles_S, nullptr));
     const int bx = (nx + kMGBX - 1) / kMGBX;
     const int want = std::max(1, (148 * 16) / bx);
     const int rows = std::max(4, (ny + want - 1) / want);
@@ -257,7 +268,8 @@ int b2s_ns2d_step(b2s_ns2d *h, b2s_ns2d_stepinfo *info)
     b2s_mg_count_launches_internal(h->mg, 3);
     if (a.implicit) {
         B2S_CHECK(b2s_mg_solve(h->mg, h->T, h->bufA, hh, cT, P.tol, P.niters, 1, &inf.r_T, &inf.cycles_T, nullptr));  // :221
-        B2S_CHECK(b2s_mg_solve(h->mg, h->W, h->bufB, hh, cW, P.tol, P.niters, 0, &inf.r_W, &inf.cycles_W, nullptr));  // :226
+        if (pcg) B2S_CHECK(b2s_mg_pcg_solve2(h->mg, h->W, h->bufB, hh, cW, P.tol, P.niters, B2S_PCG_TOL_RHS, &inf.r_W, &inf.cycles_W));
+        else B2S_CHECK(b2s_mg_solve(h->mg, h->W, h->bufB, hh, cW, P.tol, P.niters, 0, &inf.r_W, &inf.cycles_W, nullptr));  // :226
     } else {
         std::swap(h->T, h->bufA);  // T .= T + dt*(...), W .= W + dt*(...)   :229-230
         std::swap(h->W, h->bufB);

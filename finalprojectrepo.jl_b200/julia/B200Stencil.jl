@@ -303,12 +303,13 @@ end
 
 """MG-preconditioned CG (extension, no counterpart in the reference): (r_rms, iterations). The handle must have been
 created with full-weighting restriction (`opt.restriction = full_weighting`)."""
-function mg_pcg!(hd::MGHandle, u::CuArray{Float64,2}, f::CuArray{Float64,2}, h::Float64, c::Float64, tol::Float64, maxit::Int)
+function mg_pcg!(hd::MGHandle, u::CuArray{Float64,2}, f::CuArray{Float64,2}, h::Float64, c::Float64, tol::Float64, maxit::Int;
+                 relative_to_rhs::Bool=false)
     CUDA.synchronize()
     r = Ref{Cdouble}(0.0); it = Ref{Cint}(0)
-    check(ccall((:b2s_mg_pcg_solve, lib), Cint,
-                (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, Cdouble, Cdouble, Cdouble, Cint, Ref{Cdouble}, Ref{Cint}),
-                hd.ptr, u, f, h, c, tol, maxit, r, it))
+    check(ccall((:b2s_mg_pcg_solve2, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, Cdouble, Cdouble, Cdouble, Cint, Cint, Ref{Cdouble}, Ref{Cint}),
+                hd.ptr, u, f, h, c, tol, maxit, relative_to_rhs ? 1 : 0, r, it))
     return r[], Int(it[])
 end
 
@@ -435,14 +436,18 @@ Drop-in for `navier_stokes_2D(; opt, verbose, do_vis, testmode)` (scripts-part2/
 (three multigrid solves per step, the fused velocity / stencil-term kernels around them) runs inside the library on the
 current CUDA device; returns `SimOut_t` with host matrices like the reference. `W_init` supplies the field for
 `W_init_strategy = W_from_file` (the reference reads `test/reftest-files/fortran/Winit.bin`, part2.jl:67-73);
-`mgopt` selects the multigrid variant (default: the reference's damped Jacobi + injection).
+`mgopt` selects the multigrid variant (default: the reference's damped Jacobi + injection); `mg_pcg = true` solves the two
+Dirichlet systems of a step (S, W) with MG-preconditioned CG instead of plain V-cycle iteration (needs
+`mgopt.restriction = full_weighting`).
 """
-function navier_stokes_2D(; opt::SimIn_t=SimIn_t(), verbose=true, do_vis=false, testmode=false, W_init=nothing, mgopt=MGOpt())
+function navier_stokes_2D(; opt::SimIn_t=SimIn_t(), verbose=true, do_vis=false, testmode=false, W_init=nothing, mgopt=MGOpt(),
+                          mg_pcg::Bool=false)
     nx, ny = opt.nx, opt.ny
     prm = NS2DParams(opt.k, opt.Ra, opt.Pr, nx, ny, opt.ttot, opt.beta, opt.niters, opt.tol, opt.a_dif, opt.a_adv)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:b2s_ns2d_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{NS2DParams}, Ref{MGConfig}), h, prm, mgconfig(nx, ny, mgopt)))
     try
+        mg_pcg && check(ccall((:b2s_ns2d_set_solver, lib), Cint, (Ptr{Cvoid}, Cint), h[], 1))
         _ns_init!(h[], NS_FIELD_T, opt.T_init_strategy, nx, ny, nothing)
         _ns_init!(h[], NS_FIELD_W, opt.W_init_strategy, nx, ny, W_init)
         tic = 0.0; sim_time = 0.0; step = 0

@@ -125,12 +125,14 @@ class MGHandle:
                                          C.byref(r), C.byref(ms)))
         return r.value, ms.value
 
-    def pcg(self, u, f, h, c, tol, maxit):
-        """MG-preconditioned CG (extension): returns (r_rms, iterations)."""
+    def pcg(self, u, f, h, c, tol, maxit, tol_mode=capi.PCG_TOL_INITIAL_RESIDUAL):
+        """MG-preconditioned CG (extension): returns (r_rms, iterations). tol_mode: relative to the initial residual, or
+        MGsolve's criterion r_rms < tol * f_rms (capi.PCG_TOL_RHS)."""
         assert _chk(u) == (self.nx, self.ny) and _chk(f) == (self.nx, self.ny)
         _torch().cuda.current_stream().synchronize()
         r, it = C.c_double(), C.c_int()
-        capi.check(self._L.b2s_mg_pcg_solve(self._h, capi.ptr(u), capi.ptr(f), h, c, tol, int(maxit), C.byref(r), C.byref(it)))
+        capi.check(self._L.b2s_mg_pcg_solve2(self._h, capi.ptr(u), capi.ptr(f), h, c, tol, int(maxit), int(tol_mode),
+                                             C.byref(r), C.byref(it)))
         return r.value, it.value
 
     def last_coarse_sweeps(self):
@@ -287,7 +289,9 @@ SimOut_t = collections.namedtuple("SimOut_t", "T W S t_elapsed timed_iters")
 
 
 class NavierStokes2D:
-    def __init__(self, opt, mgopt=None, device=0):
+    def __init__(self, opt, mgopt=None, device=0, solver=capi.NS_SOLVER_VCYCLE):
+        """solver: NS_SOLVER_VCYCLE (the reference: plain V-cycle iteration) or NS_SOLVER_MG_PCG (MG-preconditioned CG for
+        the S and W solves; needs mgopt.restriction = full weighting)."""
         self._L = capi.lib()
         mgopt = mgopt or MGOpt()
         p = capi.NS2DParams(opt.k, opt.Ra, opt.Pr, opt.nx, opt.ny, opt.ttot, opt.beta, opt.niters, opt.tol, opt.a_dif,
@@ -298,6 +302,8 @@ class NavierStokes2D:
         self.shape = (opt.nx, opt.ny)
         self._h = C.c_void_p()
         capi.check(self._L.b2s_ns2d_create(C.byref(self._h), C.byref(p), C.byref(cfg)))
+        if solver != capi.NS_SOLVER_VCYCLE:
+            capi.check(self._L.b2s_ns2d_set_solver(self._h, int(solver)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -334,10 +340,12 @@ class NavierStokes2D:
         return info
 
 
-def navier_stokes_2D(*, opt=None, verbose=True, do_vis=False, testmode=False, mgopt=None, device=0, return_infos=False):
-    """Drop-in for part2.jl:140-262. Returns SimOut_t(T, W, S, t_elapsed, timed_iters) with host arrays."""
+def navier_stokes_2D(*, opt=None, verbose=True, do_vis=False, testmode=False, mgopt=None, device=0, return_infos=False,
+                     solver=capi.NS_SOLVER_VCYCLE):
+    """Drop-in for part2.jl:140-262. Returns SimOut_t(T, W, S, t_elapsed, timed_iters) with host arrays.
+    `solver` / `mgopt` select MG-preconditioned CG for the S and W solves (extension; default: the reference's cycling)."""
     opt = opt or SimIn_t()
-    sim = NavierStokes2D(opt, mgopt, device)
+    sim = NavierStokes2D(opt, mgopt, device, solver)
     try:
         if opt.T_init_strategy == "cosine":
             sim.init_cosine("T")
@@ -465,14 +473,14 @@ def bench_config2_matrix(device=0, n=1025, ncycles=30):
     return rows
 
 
-def bench_navier_stokes(device=0, n=2049, steps=8, seed=1):
+def bench_navier_stokes(device=0, n=2049, steps=8, seed=1, solver=capi.NS_SOLVER_VCYCLE, mgopt=None):
     """Config #4: 2-D streamfunction-vorticity Navier-Stokes, semi-implicit (beta = 0.5, Pr = 0.1, tol 1e-7: the
     published experiment's settings, part2_semi_implicit_vs_explicit_experiments.jl:38-44) on an n x n grid, W ~ U[0,1).
-    Times the steps from the 4th on (the reference starts its timer at step 3, part2.jl:182-184)."""
-    import warnings
+    Times the steps from the 4th on (the reference starts its timer at step 3, part2.jl:182-184). `solver`: plain V-cycle
+    iteration like the reference, or MG-preconditioned CG for the S and W solves (cycle-equivalents = CG iterations)."""
     torch = _torch()
     opt = SimIn_t(nx=n, ny=n, beta=0.5, Pr=0.1, tol=1.0e-7, niters=50)
-    sim = NavierStokes2D(opt, MGOpt(), device)
+    sim = NavierStokes2D(opt, mgopt or MGOpt(), device, solver)
     sim.init_cosine("T")
     sim.set_field("W", np.random.default_rng(seed).random((n, n)))
     infos, t0 = [], None
@@ -488,9 +496,10 @@ def bench_navier_stokes(device=0, n=2049, steps=8, seed=1):
     cyc = sum(a + b + c for _, a, b, c in timed)
     sim.close()
     return {"grid": [n, n], "beta": 0.5, "Pr": 0.1, "tol": 1e-7, "timed_steps": len(timed),
+            "solver": "mg_pcg (S, W) + v-cycles (T)" if solver == capi.NS_SOLVER_MG_PCG else "v-cycles (reference)",
             "ms_per_step": dt_wall / len(timed) * 1e3, "vcycles_per_step": cyc / len(timed),
             "cycles_S_T_W": [list(x[1:]) for x in infos], "dof_per_s_per_vcycle": n * n * cyc / dt_wall,
-            "note": "whole time step incl. 3 MG solves, velocity/dt reduction, fused stencil + rhs kernel; host syncs per V-cycle"}
+            "note": "whole time step incl. 3 solves, velocity/dt reduction, fused stencil + rhs kernel; wall clock"}
 
 
 def smoke_check(O):

@@ -259,6 +259,13 @@ int b2s_mg_cycles(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, d
  * Exit: sqrt(sum r^2/(nx ny)) < tol * (the same norm of the initial residual). iters = CG iterations = V-cycles. */
 int b2s_mg_pcg_solve(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, double c, double tol, int maxit,
                      double *r_rms, int *iters);
+/* The same with a selectable stopping criterion: relative to the initial residual (as above), or MGsolve_2DPoisson!'s
+ * r_rms < tol * f_rms with f_rms over all entries of f (multigrid.jl:53,70-75) -- what navier_stokes_2D needs to swap
+ * solvers without changing the accuracy it asks for. */
+#define B2S_PCG_TOL_INITIAL_RESIDUAL 0
+#define B2S_PCG_TOL_RHS 1
+int b2s_mg_pcg_solve2(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, double c, double tol, int maxit,
+                      int tol_mode, double *r_rms, int *iters);
 /* Sweeps / iterations the coarsest-level solver used in the last V-cycle. */
 int b2s_mg_last_coarse_sweeps(const b2s_mg *h, int *sweeps);
 int b2s_mg_stats(const b2s_mg *h, long long *kernel_launches, double *last_call_ms);
@@ -284,6 +291,14 @@ typedef struct {
 
 int b2s_ns2d_create(b2s_ns2d **h, const b2s_ns2d_params *p, const b2s_mg_config *mg);
 int b2s_ns2d_destroy(b2s_ns2d *h);
+/* Solver of the two Dirichlet solves of a step (S: part2.jl:187, W: :226). The reference iterates plain V-cycles
+ * (B2S_NS_SOLVER_VCYCLE, the parity default). B2S_NS_SOLVER_MG_PCG (BASELINE configs[3], north-star extension) solves them
+ * with MG-preconditioned CG under the same stopping criterion; it needs a handle whose multigrid configuration restricts
+ * with full weighting (symmetric cycle). The T solve (:221) applies boundary conditions inside the cycle -- not an SPD
+ * system -- and always iterates V-cycles. cycles_S / cycles_W of the step info then count CG iterations (= V-cycles). */
+#define B2S_NS_SOLVER_VCYCLE 0
+#define B2S_NS_SOLVER_MG_PCG 1
+int b2s_ns2d_set_solver(b2s_ns2d *h, int solver);
 /* which: 0 T, 1 W, 2 S; host arrays nx*ny column-major */
 int b2s_ns2d_set_field(b2s_ns2d *h, int which, const double *host);
 int b2s_ns2d_get_field(b2s_ns2d *h, int which, double *host);

@@ -390,6 +390,14 @@ typedef struct {
     double r_S, r_T, r_W;
 } orc_ns_stepinfo;
 
+/* Solver of the two Dirichlet solves of a step (S: part2.jl:187, W: :226): 0 = plain V-cycle iteration (the reference),
+ * 1 = MG-preconditioned CG (north-star extension) with MGsolve's stopping criterion. The T solve applies boundary
+ * conditions inside the cycle (apply_BCs = true, :221), which is not an SPD system: it always iterates V-cycles. */
+static int g_ns_solver = 0;
+void orc_ns_set_solver(int solver) { g_ns_solver = solver; }
+double orc_mg_pcg2d_mode(double *u, const double *f, double h, double c, double tol, int maxit, int nx, int ny,
+                         const orc_mg_opt *o, int *iters_out, int tol_mode);
+
 /* One time step. Work arrays are allocated inside (oracle: clarity over speed).
  * out_aux (nullable): 7 arrays nx*ny each: vx, vy, v, Ra_dTdx, dT2, dW2, (unused) */
 void orc_ns_step(const orc_ns_params *P, const orc_mg_opt *o, double *S, double *T, double *W,
@@ -404,7 +412,8 @@ void orc_ns_step(const orc_ns_params *P, const orc_mg_opt *o, double *S, double 
     double *dW2 = (double *)calloc(n, 8), *dWx = (double *)calloc(n, 8), *dWy = (double *)calloc(n, 8);
     double *Ra_dTdx = (double *)calloc(n, 8), *rhs = (double *)calloc(n, 8);
 
-    info->r_S = orc_mgsolve2d(S, W, h, 0.0, P->tol, P->niters, 0, nx, ny, o, &info->cycles_S, NULL);
+    if (g_ns_solver == 1) info->r_S = orc_mg_pcg2d_mode(S, W, h, 0.0, P->tol, P->niters, nx, ny, o, &info->cycles_S, 1);
+    else info->r_S = orc_mgsolve2d(S, W, h, 0.0, P->tol, P->niters, 0, nx, ny, o, &info->cycles_S, NULL);
     /* part2.jl:90-96 */
     for (int j = 1; j < ny - 1; ++j)
         for (int i = 1; i < nx - 1; ++i) {
@@ -457,7 +466,8 @@ void orc_ns_step(const orc_ns_params *P, const orc_mg_opt *o, double *S, double 
         c = c / P->Pr;
         for (size_t p = 0; p < n; ++p)
             rhs[p] = -c * (W[p] + dt * ((((1.0 - P->beta) * dW2[p] - dWx[p]) - dWy[p]) - P->Pr * Ra_dTdx[p]));
-        info->r_W = orc_mgsolve2d(W, rhs, h, c, P->tol, P->niters, 0, nx, ny, o, &info->cycles_W, NULL);
+        if (g_ns_solver == 1) info->r_W = orc_mg_pcg2d_mode(W, rhs, h, c, P->tol, P->niters, nx, ny, o, &info->cycles_W, 1);
+        else info->r_W = orc_mgsolve2d(W, rhs, h, c, P->tol, P->niters, 0, nx, ny, o, &info->cycles_W, NULL);
     } else {
         for (size_t p = 0; p < n; ++p) T[p] = T[p] + dt * ((dT2[p] - dTx[p]) - dTy[p]);
         for (size_t p = 0; p < n; ++p) W[p] = W[p] + dt * (((dW2[p] - dWx[p]) - dWy[p]) - P->Pr * Ra_dTdx[p]);
@@ -481,13 +491,22 @@ void orc_ns_step(const orc_ns_params *P, const orc_mg_opt *o, double *S, double 
 double orc_mg_pcg2d(double *u, const double *f, double h, double c, double tol, int maxit, int nx, int ny,
                     const orc_mg_opt *o, int *iters_out)
 {
+    return orc_mg_pcg2d_mode(u, f, h, c, tol, maxit, nx, ny, o, iters_out, 0);
+}
+
+/* tol_mode 0: exit relative to the initial residual (above); 1: MGsolve's criterion r_rms < tol * f_rms with
+ * f_rms = sqrt(sum(f.^2)/(nx*ny)) over ALL entries (multigrid.jl:53,70-75). */
+double orc_mg_pcg2d_mode(double *u, const double *f, double h, double c, double tol, int maxit, int nx, int ny,
+                         const orc_mg_opt *o, int *iters_out, int tol_mode)
+{
     size_t n = (size_t)nx * ny;
     double *r = (double *)calloc(n, 8), *z = (double *)calloc(n, 8), *p = (double *)calloc(n, 8), *q = (double *)calloc(n, 8);
     orc_matvec2d(u, h, h, c, q, nx, ny);
     for (int j = 1; j < ny - 1; ++j)
         for (int i = 1; i < nx - 1; ++i) r[IDX(i, j)] = f[IDX(i, j)] - q[IDX(i, j)];
     const double N = (double)nx * ny;
-    const double tolf = tol * sqrt(sumsq(r, nx, ny) / N);  /* relative to the initial residual */
+    const double tolf = tol_mode == 1 ? tol * sqrt(sumsq(f, nx, ny) / N)  /* relative to f_rms */
+                                      : tol * sqrt(sumsq(r, nx, ny) / N); /* relative to the initial residual */
     double r_rms = sqrt(sumsq(r, nx, ny) / N);
     int it = 0;
     double rz = 0.0;

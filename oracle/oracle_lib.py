@@ -108,6 +108,8 @@ def lib():
                                     C.POINTER(MGOpt), _ip, _dp]
         L.orc_mg_pcg2d.restype = C.c_double
         L.orc_mg_pcg2d.argtypes = [_dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(MGOpt), _ip]
+        L.orc_ns_set_solver.argtypes = [C.c_int]
+        L.orc_ns_set_solver.restype = None
         L.orc_ns_init_cosine.argtypes = [_dp, C.c_int, C.c_int]
         L.orc_ns_step.argtypes = [C.POINTER(NSParams), C.POINTER(MGOpt), _dp, _dp, _dp, C.POINTER(NSStepInfo), _dp]
         _LIB = L
@@ -259,9 +261,11 @@ def mg_pcg2d(u, f, h, c, tol, maxit, opt=None):
     return r, it.value
 
 
-def ns_step(params, S, T, W, opt=None, want_aux=False):
+def ns_step(params, S, T, W, opt=None, want_aux=False, solver=0):
+    """solver: 0 plain V-cycle iteration (the reference), 1 MG-preconditioned CG for the S and W solves (extension)."""
     opt = opt or MGOpt()
     info = NSStepInfo()
+    lib().orc_ns_set_solver(int(solver))
     aux = np.zeros(7 * S.size) if want_aux else None
     lib().orc_ns_step(C.byref(params), C.byref(opt), _p(S), _p(T), _p(W), C.byref(info),
                       aux.ctypes.data_as(_dp) if want_aux else None)

@@ -468,3 +468,37 @@ def test_navier_stokes_2049_step_vs_oracle(p2, oracle):
     for name, ref in (("S", S), ("T", T), ("W", W)):
         assert np.array_equal(sim.get_field(name), ref), name
     sim.close()
+
+
+def test_navier_stokes_with_mg_pcg_solver(p2, oracle):
+    """f2 / BASELINE configs[3]: MG-preconditioned CG as the solver of the S and W solves of navier_stokes_2D (the T solve
+    keeps cycling: BCs inside the cycle). No reference implementation -> against the oracle: identical iteration counts,
+    fields to 1e-9 relative (the dot products are summed in a different order), and fewer V-cycles than plain cycling."""
+    from b200stencil import capi
+    nx, ny = 257, 65
+    W0 = rnd((nx, ny), 31)
+    P = oracle.NSParams(nx=nx, ny=ny, beta=0.5, Pr=0.1, tol=1e-7)
+    oo = oracle.MGOpt(restriction=1)
+    S, T, W = oracle.farray((nx, ny)), oracle.ns_init_cosine(nx, ny), W0.copy(order="F")
+    sim = p2.NavierStokes2D(p2.SimIn_t(nx=nx, ny=ny, beta=0.5, Pr=0.1, tol=1e-7), mgopt=p2.MGOpt(restriction=1),
+                            solver=capi.NS_SOLVER_MG_PCG)
+    plain = p2.NavierStokes2D(p2.SimIn_t(nx=nx, ny=ny, beta=0.5, Pr=0.1, tol=1e-7))
+    for s_ in (sim, plain):
+        s_.init_cosine("T")
+        s_.set_field("W", W0)
+    tot_pcg = tot_plain = 0
+    for step in range(3):
+        io, _ = oracle.ns_step(P, S, T, W, opt=oo, solver=1)
+        ig, ip = sim.step(), plain.step()
+        assert (ig.cycles_S, ig.cycles_T, ig.cycles_W) == (io.cycles_S, io.cycles_T, io.cycles_W), step
+        for name, ref in (("S", S), ("T", T), ("W", W)):
+            assert np.max(np.abs(sim.get_field(name) - ref)) <= 1e-9 * np.max(np.abs(ref)), (step, name)
+        tot_pcg += ig.cycles_S + ig.cycles_W
+        tot_plain += ip.cycles_S + ip.cycles_W
+    assert tot_pcg < tot_plain
+    sim.close(); plain.close()
+    bad = p2.NavierStokes2D(p2.SimIn_t(nx=nx, ny=ny, beta=0.5), solver=capi.NS_SOLVER_MG_PCG)  # injection: not symmetric
+    bad.init_cosine("T")
+    with pytest.raises(capi.B2SError):
+        bad.step()
+    bad.close()

@@ -290,9 +290,9 @@ def test_julia_ccall_signatures_match_header():
         seen.add(name)
     # the entry points of SURVEY 8(b) are all reachable from Julia
     for need in ("b2s_diff3d_create", "b2s_diff3d_solve_timestep", "b2s_diff3d_gather", "b2s_diff3d_ipc_connect",
-                 "b2s_diffusion3d_step_tau", "b2s_mg_create", "b2s_mg_solve", "b2s_mg_vcycle", "b2s_mg_pcg_solve", "b2s_cg_solve",
+                 "b2s_diffusion3d_step_tau", "b2s_mg_create", "b2s_mg_solve", "b2s_mg_vcycle", "b2s_mg_pcg_solve2", "b2s_cg_solve",
                  "b2s_iteration2d", "b2s_residual2d", "b2s_restrict_inject2d", "b2s_prolongate2d", "b2s_matvec2d",
-                 "b2s_apply_bc2d", "b2s_ns2d_create", "b2s_ns2d_step", "b2s_ns2d_get_field", "b2s_ns2d_set_field"):
+                 "b2s_apply_bc2d", "b2s_ns2d_create", "b2s_ns2d_set_solver", "b2s_ns2d_step", "b2s_ns2d_get_field", "b2s_ns2d_set_field"):
         assert need in seen, need
     for fn in ("diffusion_3D_kernel_programming", "diffusion_3D_array_programming", "main", "MGsolve_2DPoisson!",
                "Vcycle_2DPoisson!", "iteration_2DPoisson!", "residual_2DPoisson_wrapper!", "restrict_wrapper!",
