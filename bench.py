@@ -247,6 +247,32 @@ def mg_bench(device, peak):
     return out
 
 
+def mg_roofline_summary(mg):
+    """Config #2 as a first-class roofline: per grid size the V-cycle against ONE byte model (the fused kernels' compulsory
+    54 B per point of every non-coarsest level) and its dominant kernel, timed in isolation with CUDA events inside the
+    library; `traffic` = DRAM bytes per launch of that kernel from the ncu --set full capture under profiles/ (or null)."""
+    out = {}
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    for n, v in (mg.get("sizes") or {}).items():
+        r = v.get("roofline")
+        if not r:
+            continue
+        d = r.get("dominant_kernel") or {}
+        key = f"mg_{d.get('kernel')}_level{d.get('level')}_{n}_bytes_per_launch"
+        out[n] = {"metric": "mg_vcycle_dof_per_s", "value": v["dof_per_s"], "unit": "DoF/s per V-cycle",
+                  "ms_per_vcycle": v["ms_per_vcycle"], "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"],
+                  "unit_roofline": "GB/s", "frac": r["frac"], "model": r["model"],
+                  "dominant_kernel": {"name": d.get("name"), "level": d.get("level"), "avg_launch_ms": d.get("ms"),
+                                      "algorithmic_bytes_per_launch": d.get("algorithmic_bytes"),
+                                      "achieved": d.get("achieved_gbs"), "frac": d.get("frac_of_hbm_peak"),
+                                      "traffic": traffic.get(key)}}
+    return out
+
+
 def mg_cpu_baseline(n):
     """The reference's CPU (Threads) multigrid path -- the OpenMP oracle port with the reference's un-fused passes -- on the
     same bench shape (multigrid_bench.jl: x = 0, b ~ U[0,1), tol 1e-6), timed on the host cores of this box."""
@@ -494,6 +520,7 @@ def _finish(args, rank, N, n, dev, peak, value, ms_per_step, wall, roofline, e2e
             out["cpu_baseline"] = cpu
         if mg is not None:
             out["mg"] = mg
+            out["mg_roofline"] = mg_roofline_summary(mg)
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()

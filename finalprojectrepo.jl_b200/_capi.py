@@ -117,6 +117,7 @@ SIGNATURES = {
     "b2s_mg_cycles": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _i, _dp, _dp]),
     "b2s_mg_pcg_solve": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _dp, _ip]),
     "b2s_mg_pcg_solve2": (_i, [_vp, _vp, _vp, _d, _d, _d, _i, _i, _dp, _ip]),
+    "b2s_mg_profile_kernels": (_i, [_vp, _vp, _vp, _d, _d, _i, _ip, _dp, _dp, _dp, _ip, _ip]),
     "b2s_mg_last_coarse_sweeps": (_i, [_vp, _ip]),
     "b2s_mg_stats": (_i, [_vp, _llp, _dp]),
     "b2s_cg_solve": (_i, [_vp, _vp, _d, _d, _d, _d, _i, _i, _i, _i, _dp, _ip, _vp]),

@@ -194,7 +194,7 @@ struct Arena {  // layout of the per-slab device allocation (identical on every 
         off_peer_table = o; o += align_up(sizeof(void *) * kMaxRanks, 1024);
         off_cart = o; o += align_up(sizeof(CartSync), 1024);
         off_cart_table = o; o += align_up(sizeof(void *) * kMaxRanks, 1024);
-        off_flags = o; o += align_up(4 * max_tiles * sizeof(unsigned long long), 1024);  // halo flags [4][max_tiles]
+        off_flags = o; o += align_up(2 * max_tiles * sizeof(unsigned long long), 1024);  // halo flags [2][max_tiles]
         bytes = o;
     }
 };
@@ -212,7 +212,7 @@ struct Slab {
     // neighbours' buffers (local pointer, peer pointer or IPC mapping); nullptr at the ends of the slab stack
     double *lo_buf[2] = {nullptr, nullptr}, *hi_buf[2] = {nullptr, nullptr};
     PTState *state = nullptr;                      // this slab's own PT state (z-slab stacks; cart handles share one per device)
-    unsigned long long *flags = nullptr;           // my halo flags [4][ntiles]
+    unsigned long long *flags = nullptr;           // my halo flags [2][ntiles]
     unsigned long long *lo_flags = nullptr, *hi_flags = nullptr;  // the z neighbours' flag arrays (local, peer or IPC pointers)
     RankSlots **table = nullptr;                   // device array: every rank's mailbox (z-slab stacks)
     double *staging = nullptr;  // next job's state (b2s_diff3d_upload_state_async), allocated on first use

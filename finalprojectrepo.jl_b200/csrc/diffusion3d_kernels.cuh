@@ -76,9 +76,10 @@ __device__ __forceinline__ bool slot_consume(const RankSlots *mine, int gen, int
 
 // z-slab stacks: per-tile halo flags in every rank's arena, written by the two z neighbours (peer stores), read locally.
 // A flag holds the sequence number of the neighbour's step kernel that set it (monotonic, never reset).
-//   kFlagInLo / kFlagInHi  : the low / high neighbour has stored this tile of my plane 0 / nz-1          (data ready)
-//   kFlagAckLo / kFlagAckHi: the low / high neighbour has read the tile I stored into its plane nz-1 / 0 (free to overwrite)
-enum { kFlagInLo = 0, kFlagInHi = 1, kFlagAckLo = 2, kFlagAckHi = 3 };
+//   kFlagLo / kFlagHi: the block of the low / high neighbour that owns this tile of the adjacent z chunk has finished its
+//   kernel `value`: it has stored its boundary plane into my halo plane (data ready) AND it has read the plane I stored
+//   into its halo plane one kernel earlier (free to overwrite) -- one flag serves both directions of the dependency.
+enum { kFlagLo = 0, kFlagHi = 1 };
 
 // General decompositions with one process per GPU: phase mailbox in every rank's arena. phase[r] is the last phase rank r
 // has completed (4*seq + k: k-th barrier of the PT iteration with sequence number seq), written by rank r itself.
@@ -156,11 +157,13 @@ __device__ __forceinline__ double cell_residual_flux(double qx_lo, double qx_hi,
 
 // ---- Halo flags: the z-slab protocol -----------------------------------------------------------------------------
 // No rank ever waits for ALL ranks on the critical path. Kernel number s (PTState::seq, identical on all ranks) of a rank
-//   * reads its halo planes 0 / nz-1 of Htau, which the neighbour's kernel s-1 has stored  -> wait in[t]  >= s-1  (RAW)
-//   * stores planes into the neighbour's Htau2 halo, which the neighbour's kernel s-1 read -> wait ack[t] >= s-1  (WAR)
-// per xy tile t, only in the blocks that own the first / last z chunk (they are scheduled first, so a neighbour that is
-// up to ~3/4 of a kernel behind never stalls anybody), and signals in[t] = s / ack[t] = s in the neighbour's arena when
-// the block is done (one __syncthreads, one system fence and <= 4 flag stores by one thread; no other block fences).
+//   * reads its halo planes 0 / nz-1 of Htau, which the neighbour's kernel s-1 has stored   (RAW)
+//   * stores planes into the neighbour's Htau2 halo, which the neighbour's kernel s-1 read  (WAR)
+// Both hold once the neighbour's block that owns the same xy tile t of the adjacent z chunk has finished kernel s-1, so
+// the blocks that own the first / last z chunk wait for flag[t] >= s-1 (one acquire load by one thread) and store
+// flag[t] = s into the neighbour's arena when they are done (one __syncthreads, one system fence, one 8-byte store by
+// one thread; no other block fences). They are scheduled right after the first interior blocks, so their planes reach
+// the neighbour within the first quarter of the kernel and a neighbour that is up to ~3/4 of a kernel behind never stalls anybody.
 // All waits refer to strictly earlier kernels, so every rank makes progress independently of co-residency.
 // The global norm is evaluated one kernel late: the last block of kernel s publishes its partial (as before) and then
 // consumes the partials of kernel s-1, which every rank published a whole kernel ago. If that test ends the PT loop,
@@ -184,14 +187,8 @@ __device__ __forceinline__ void halo_flags_wait(const StepParams &p, int tile, b
 {
     bool ok = true;
     const unsigned long long want = seq - 1;
-    if (first_chunk && p.push_lo != nullptr) {
-        ok &= flag_wait(p.flags + (size_t)kFlagInLo * p.ntiles + tile, want, p.timeout_cycles);
-        ok &= flag_wait(p.flags + (size_t)kFlagAckLo * p.ntiles + tile, want, p.timeout_cycles);
-    }
-    if (last_chunk && p.push_hi != nullptr) {
-        ok &= flag_wait(p.flags + (size_t)kFlagInHi * p.ntiles + tile, want, p.timeout_cycles);
-        ok &= flag_wait(p.flags + (size_t)kFlagAckHi * p.ntiles + tile, want, p.timeout_cycles);
-    }
+    if (first_chunk && p.push_lo != nullptr) ok &= flag_wait(p.flags + (size_t)kFlagLo * p.ntiles + tile, want, p.timeout_cycles);
+    if (last_chunk && p.push_hi != nullptr) ok &= flag_wait(p.flags + (size_t)kFlagHi * p.ntiles + tile, want, p.timeout_cycles);
     if (!ok) { p.state->error = 1; }
     fence_proxy_async_all();  // the planes are fetched by TMA (async proxy) after this generic-proxy acquire
 }
@@ -203,21 +200,18 @@ __device__ __forceinline__ void halo_flags_signal(const StepParams &p, int tile,
     __syncthreads();
     if (tid != 0) return;
     __threadfence_system();
-    if (first_chunk && p.push_lo != nullptr) {
-        st_release_sys_u64(p.lo_flags + (size_t)kFlagInHi * p.ntiles + tile, seq);   // its plane nz-1 holds my tile
-        st_release_sys_u64(p.lo_flags + (size_t)kFlagAckHi * p.ntiles + tile, seq);  // I have read what it stored into my plane 0
-    }
-    if (last_chunk && p.push_hi != nullptr) {
-        st_release_sys_u64(p.hi_flags + (size_t)kFlagInLo * p.ntiles + tile, seq);
-        st_release_sys_u64(p.hi_flags + (size_t)kFlagAckLo * p.ntiles + tile, seq);
-    }
+    // to the low neighbour I am its HIGH neighbour: its plane nz-1 holds my tile, and I have read what it stored into my plane 0
+    if (first_chunk && p.push_lo != nullptr) st_relaxed_sys_u64(p.lo_flags + (size_t)kFlagHi * p.ntiles + tile, seq);
+    if (last_chunk && p.push_hi != nullptr) st_relaxed_sys_u64(p.hi_flags + (size_t)kFlagLo * p.ntiles + tile, seq);
 }
 
-// boundary chunks first: grid z index -> z chunk
+// grid z index -> z chunk: one interior chunk first, then the two boundary chunks, then the rest. The boundary blocks
+// start as soon as the first blocks retire (their planes reach the neighbour within the first quarter of the kernel), and
+// their flag polls and system fences always overlap with an interior block resident on the same SM.
 __device__ __forceinline__ int chunk_of_block(const StepParams &p, int bz, int nchunks)
 {
-    if (!p.flagged) return bz;
-    return bz == 0 ? 0 : (bz == 1 ? nchunks - 1 : bz - 1);
+    if (!p.flagged || nchunks < 3) return bz;
+    return bz == 0 ? 1 : (bz == 1 ? 0 : (bz == 2 ? nchunks - 1 : bz - 1));
 }
 
 // Shared tail of both kernel variants: block partial -> deterministic grid sum -> (optionally) exit test / publish.

@@ -199,15 +199,18 @@ int coarse_global_solve(b2s_mg *h, cudaStream_t st, long long *count);
 int cg_global(double *x_in, const double *b, double *work, double hx, double hy, double c, double tol, int nmax, int nx, int ny,
               cudaStream_t st, double *ss_out, int *iters_out, long long *count);
 
-// Enqueues one V-cycle (multigrid.jl:91-170) on `st`; counts kernel launches.
-int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
+// Enqueues one V-cycle (multigrid.jl:91-170) on `st`; counts kernel launches. only_level >= 0 (profiling, fused paths):
+// emit just one kernel of the cycle -- the downward (only_dir 0) or upward (1) kernel of that level, or the kernel that
+// handles everything below the global-memory levels (2: collapsed coarse kernel / cluster kernel).
+int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc, int only_level = -1, int only_dir = 0)
 {
+    auto skip = [&](int l, int dir) { return only_level >= 0 && !(dir == only_dir && (dir == 2 || l == only_level)); };
     const b2s_mg_config &c = h->cfg;
     const MGCall *cp = h->call_dev;
     long long n = 0;
     const bool rb = c.smoother == B2S_SMOOTH_RBGS;
     // apply_boundary_conditions!(u) before the cycle (multigrid.jl:60-62); calls without it use a graph without the node
-    if (with_bc) {
+    if (with_bc && only_level < 0) {
         const int t = h->nx[0] + h->ny[0];
         mg_bc_kernel<<<(t + 255) / 256, 256, 0, st>>>(cp, nullptr, h->nx[0], h->ny[0], 0);
         ++n;
@@ -328,6 +331,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
     };
     auto stream_grid = [&](int l, int ch) { return dim3((h->nx[l] + kSW - 1) / kSW, (h->ny[l] + ch - 1) / ch, 1); };
     for (int l = 0; l < fs && fused; ++l) {
+        if (skip(l, 0)) continue;
         TileArgs t = tile_args(l);
         t.u_in = h->u[l]; t.u_out = h->tmp[l]; t.rc = h->rhs[l + 1]; t.ec = h->u[l + 1];
         if (fused_b) {
@@ -357,7 +361,8 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
         ++n;
     }
     // coarsest level in global memory (too large for shared memory)
-    if (h->coarse_global) {
+    if (skip(0, 2)) {
+    } else if (h->coarse_global) {
         long long nn = 0;
         B2S_CHECK(coarse_global_solve(h, st, &nn));
         n += nn;
@@ -404,9 +409,10 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
     }
     // upward leg
     for (int l = fs - 1; l >= 0 && fused; --l) {
+        if (skip(l, 1)) continue;
         TileArgs t = tile_args(l);
         t.u_in = h->tmp[l]; t.u_out = h->u[l]; t.ec = h->u[l + 1]; t.want_norm = (l == 0);
-        t.fused_end = (l == 0 && end_fused) ? 1 : 0;
+        t.fused_end = (l == 0 && end_fused && only_level < 0) ? 1 : 0;
         if (fused_b) {
             launch_rb_tile(rb_choice(l), true, t, st);
         } else if (use_streaming(l) && warp_kind) {
@@ -449,7 +455,7 @@ int enqueue_vcycle(b2s_mg *h, cudaStream_t st, long long *count, bool with_bc)
             ++n;
         }
     }
-    if (!end_fused) {
+    if (!end_fused && only_level < 0) {
         mg_cycle_end_kernel<<<1, 32, 0, st>>>(h->call_dev);  // r_rms, exit test, bookkeeping (multigrid.jl:64-75)
         ++n;
     }
@@ -1044,6 +1050,43 @@ int b2s_mg_pcg_solve2(b2s_mg *h, double *u, const double *f, double hgrid, doubl
     h->last_ms = ms;
     if (r_rms_out) *r_rms_out = r_rms;
     if (iters_out) *iters_out = it;
+    return B2S_OK;
+}
+
+int b2s_mg_profile_kernels(b2s_mg *h, double *u, const double *f, double hgrid, double c, int reps, int *nlevels_out,
+                           double *ms_down, double *ms_up, double *ms_tail, int *level_nx, int *level_ny)
+{
+    B2S_REQUIRE(h && u && f && reps >= 1 && nlevels_out && ms_down && ms_up && ms_tail, B2S_ERR_BAD_ARG, "bad argument");
+    B2S_REQUIRE(fused_variant_a(h->cfg) || fused_variant_b(h->cfg), B2S_ERR_BAD_ARG, "profiling needs the fused level kernels");
+    DeviceGuard guard;
+    guard.set(h->cfg.device);
+    const bool use_mid = !h->coarse_global && h->mid_nc > 0 && h->mid_first < h->first_smem;
+    const int fs = h->coarse_global ? h->nlev - 1 : (use_mid ? h->mid_first : h->first_smem);
+    B2S_CHECK(set_call(h, u, f, hgrid, c, 1e-6, 0, 0, 1 << 30, 0));
+    {  // one whole cycle first: every level array holds representative data
+        long long n = 0;
+        B2S_CHECK(enqueue_vcycle(h, h->stream, &n, false));
+    }
+    auto time_one = [&](int level, int dir, double *out) -> int {
+        long long n = 0;
+        for (int i = 0; i < 3; ++i) B2S_CHECK(enqueue_vcycle(h, h->stream, &n, false, level, dir));  // warm-up
+        B2S_CUDA(cudaEventRecord(h->ev0, h->stream));
+        for (int i = 0; i < reps; ++i) B2S_CHECK(enqueue_vcycle(h, h->stream, &n, false, level, dir));
+        B2S_CUDA(cudaEventRecord(h->ev1, h->stream));
+        B2S_CUDA(cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        B2S_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *out = (double)ms / reps;
+        return B2S_OK;
+    };
+    for (int l = 0; l < fs; ++l) {
+        B2S_CHECK(time_one(l, 0, ms_down + l));
+        B2S_CHECK(time_one(l, 1, ms_up + l));
+        if (level_nx) level_nx[l] = h->nx[l];
+        if (level_ny) level_ny[l] = h->ny[l];
+    }
+    B2S_CHECK(time_one(0, 2, ms_tail));
+    *nlevels_out = fs;
     return B2S_OK;
 }
 

@@ -135,6 +135,23 @@ class MGHandle:
                                              C.byref(r), C.byref(it)))
         return r.value, it.value
 
+    def profile_kernels(self, u, f, h, c, reps=20):
+        """Average device time (ms) of every kernel of one fused V-cycle in isolation (b2s_mg_profile_kernels):
+        [{"kernel": "down"|"up"|"tail", "level": l, "grid": [nx, ny], "ms": t}, ...]."""
+        _torch().cuda.current_stream().synchronize()
+        nl = C.c_int()
+        md, mu = (C.c_double * 24)(), (C.c_double * 24)()
+        mt = C.c_double()
+        lx, ly = (C.c_int * 24)(), (C.c_int * 24)()
+        capi.check(self._L.b2s_mg_profile_kernels(self._h, capi.ptr(u), capi.ptr(f), h, c, int(reps), C.byref(nl), md, mu,
+                                                  C.byref(mt), lx, ly))
+        out = []
+        for l in range(nl.value):
+            out.append({"kernel": "down", "level": l, "grid": [lx[l], ly[l]], "ms": md[l]})
+            out.append({"kernel": "up", "level": l, "grid": [lx[l], ly[l]], "ms": mu[l]})
+        out.append({"kernel": "tail", "level": nl.value, "grid": None, "ms": mt.value})
+        return out
+
     def last_coarse_sweeps(self):
         n = C.c_int()
         capi.check(self._L.b2s_mg_last_coarse_sweeps(self._h, C.byref(n)))
@@ -439,6 +456,30 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
             e2e_s = min(e2e_s, time.perf_counter() - t0)
         per = ms / ncycles * 1e-3
         ab = mg_algorithmic_bytes(n, n)
+        # Per kernel, in isolation (CUDA events, 20 back-to-back launches): the fused formulation's compulsory traffic is
+        # 28 B per point of the level for the downward kernel (read u, f; write u_s, rc/4, ec/4) and 26 B for the upward
+        # one (read u_s, f, ec/4; write u) -- THE byte model of every fraction below; levels whose arrays fit the 126 MB
+        # L2 (<= 2049^2) are served from L2, so their fraction of the HBM peak is a lower bound on what limits them.
+        kernels, dominant = [], None
+        try:
+            x.zero_()
+            for k in hd.profile_kernels(x, b, h, 0.0):
+                if k["kernel"] == "tail":
+                    k.update(name="mg_mid_cluster_kernel / mg_coarse_kernel (all levels below, resident in shared memory)",
+                             algorithmic_bytes=0.0, achieved_gbs=None, frac_of_hbm_peak=None, bound="latency")
+                else:
+                    pts = float(k["grid"][0]) * k["grid"][1]
+                    by = (28.0 if k["kernel"] == "down" else 26.0) * pts
+                    streaming = pts > 1.5e6 and (opt is None or opt.smoother == 0)
+                    k.update(name=("mg_%s_stream2_kernel" if streaming else "mg_%s_kernel<tile>") % k["kernel"]
+                             if (opt is None or opt.smoother == 0) else "mg_%s_rb_kernel<tile>" % k["kernel"],
+                             algorithmic_bytes=by, achieved_gbs=by / (k["ms"] * 1e-3) / 1e9,
+                             frac_of_hbm_peak=by / (k["ms"] * 1e-3) / 1e9 / hbm_peak_gbs,
+                             bound="hbm" if pts * 8 * 3 > 126e6 else "l2-resident / latency")
+                kernels.append(k)
+            dominant = max(kernels, key=lambda k: k["ms"])
+        except Exception as e:  # pragma: no cover
+            kernels = [{"unavailable": f"{type(e).__name__}: {e}"}]
         out["sizes"][str(n)] = {"dof_per_s": n * n / per, "ms_per_vcycle": per * 1e3,
                                 "ms_per_vcycle_min_max_of_5": [min(times) / ncycles, max(times) / ncycles],
                                 "vcycles_to_1e-6": nc,
@@ -447,11 +488,19 @@ def bench_vcycle(device=0, hbm_peak_gbs=6527.8, sizes=(1025, 2049, 4097), ncycle
                                     "solve_ms": e2e_s * 1e3, "dof_per_s_per_vcycle": n * n * nc / e2e_s,
                                     "h2d_bytes": n * n * 8, "d2h_bytes": n * n * 8,
                                     "what": "pinned host rhs -> device, MGsolve to 1e-6, solution -> pinned host (best of 3)"},
-                                "algorithmic_bytes_per_vcycle": ab,
-                                "achieved_gbs": ab / per / 1e9, "frac_of_hbm_peak": ab / per / 1e9 / hbm_peak_gbs,
-                                "fused_min_bytes_per_vcycle": mg_fused_min_bytes(n, n),
-                                "fused_achieved_gbs": mg_fused_min_bytes(n, n) / per / 1e9,
-                                "fused_frac_of_hbm_peak": mg_fused_min_bytes(n, n) / per / 1e9 / hbm_peak_gbs,
+                                # one byte model for every fraction: the fused formulation's compulsory 54 B per point of
+                                # every non-coarsest level (28 down + 26 up)
+                                "roofline": {"bound": "hbm" if n * n * 8 * 3 > 126e6 else "latency (arrays are L2-resident)",
+                                             "model": "fused: 54 B per point of every non-coarsest level per V-cycle",
+                                             "algorithmic_bytes_per_vcycle": mg_fused_min_bytes(n, n),
+                                             "achieved": mg_fused_min_bytes(n, n) / per / 1e9, "peak": hbm_peak_gbs,
+                                             "unit": "GB/s", "frac": mg_fused_min_bytes(n, n) / per / 1e9 / hbm_peak_gbs,
+                                             "dominant_kernel": dominant, "kernels": kernels,
+                                             "sum_of_isolated_kernels_ms": sum(k.get("ms", 0.0) for k in kernels)},
+                                # SURVEY 8d's un-fused accounting (132 B per point: one pass per sweep). The fused kernels do
+                                # not make those passes, so this is an EFFECTIVE rate for comparison with un-fused
+                                # implementations, not a fraction of any hardware peak.
+                                "survey_model_bytes_per_vcycle": ab, "survey_model_effective_gbs": ab / per / 1e9,
                                 "kernel_launches_per_vcycle": (l1 - l0) / ncycles}
         hd.close()
     return out

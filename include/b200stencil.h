@@ -266,6 +266,13 @@ int b2s_mg_pcg_solve(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid
 #define B2S_PCG_TOL_RHS 1
 int b2s_mg_pcg_solve2(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, double c, double tol, int maxit,
                       int tol_mode, double *r_rms, int *iters);
+/* Measurement aid (no reference counterpart): average device time (ms, CUDA events on the handle's stream, `reps` back-to-back
+ * launches after a warm-up) of every kernel of one V-cycle of the fused paths in isolation: per global-memory level l the
+ * downward kernel (2 sweeps + residual + restriction) and the upward kernel (prolongation + correction + 2 sweeps), and the
+ * one kernel that handles all levels below them (ms_tail). nlevels = number of global-memory levels; the ms_* / level_*
+ * arrays need capacity 24. */
+int b2s_mg_profile_kernels(b2s_mg *h, double *u_dev, const double *f_dev, double hgrid, double c, int reps, int *nlevels,
+                           double *ms_down, double *ms_up, double *ms_tail, int *level_nx, int *level_ny);
 /* Sweeps / iterations the coarsest-level solver used in the last V-cycle. */
 int b2s_mg_last_coarse_sweeps(const b2s_mg *h, int *sweeps);
 int b2s_mg_stats(const b2s_mg *h, long long *kernel_launches, double *last_call_ms);
