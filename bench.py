@@ -238,6 +238,9 @@ def mg_bench(device, peak):
         from b200stencil import capi as _capi
         out["navier_stokes_2049_mg_pcg"] = part2.bench_navier_stokes(device=device, solver=_capi.NS_SOLVER_MG_PCG,
                                                                      mgopt=part2.MGOpt(restriction=1))
+        # ... and with the variant-B cycle (red-black Gauss-Seidel + full weighting: fused level kernels) as preconditioner
+        out["navier_stokes_2049_mg_pcg_rbgs"] = part2.bench_navier_stokes(device=device, solver=_capi.NS_SOLVER_MG_PCG,
+                                                                          mgopt=part2.MGOpt(smoother=1, restriction=1))
     except Exception as e:  # pragma: no cover
         out["navier_stokes_2049_mg_pcg"] = {"unavailable": f"{type(e).__name__}: {e}"}
     try:

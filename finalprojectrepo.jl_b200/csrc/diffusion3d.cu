@@ -49,12 +49,16 @@ static int launch_tma_t(const CUtensorMap &mA, const CUtensorMap &mH, const Step
     B2S_CUDA(cudaGetDevice(&dev));
     const size_t smem = C::smem_bytes(S);
     if (!attr_set[dev & 63]) {
-        B2S_CUDA(cudaFuncSetAttribute(step_tma_kernel<TX, TY, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2S_CUDA(cudaFuncSetAttribute(step_tma_kernel<TX, TY, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2S_CUDA(cudaFuncSetAttribute(step_tma_kernel<TX, TY, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev & 63] = true;
     }
     dim3 block(TX / 2, TY, 1);
     dim3 grid((p.nx + TX - 1) / TX, (p.ny + TY - 1) / TY, (p.nz - 2 + p.zchunk - 1) / p.zchunk);
-    step_tma_kernel<TX, TY, S><<<grid, block, smem, st>>>(mA, mH, p);
+    static const bool force_multi = env_int("B2S_FORCE_MULTI_KERNEL", 0) != 0;  // A/B: the exchange-capable instantiation on one slab
+    const bool multi = force_multi || p.flagged || p.push_lo != nullptr || p.push_hi != nullptr || p.peer_slots != nullptr;
+    if (multi) step_tma_kernel<TX, TY, S, true><<<grid, block, smem, st>>>(mA, mH, p);
+    else step_tma_kernel<TX, TY, S, false><<<grid, block, smem, st>>>(mA, mH, p);
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
 }

@@ -215,6 +215,7 @@ __device__ __forceinline__ int chunk_of_block(const StepParams &p, int bz, int n
 }
 
 // Shared tail of both kernel variants: block partial -> deterministic grid sum -> (optionally) exit test / publish.
+template <bool MULTI = true>
 __device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, double *red, unsigned long long seq)
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
@@ -226,15 +227,22 @@ __device__ __forceinline__ void step_epilogue(const StepParams &p, double acc, d
     // ---- last block of the grid (all its threads; `total` is valid in thread 0) ----
     if (tid == 0) {
         if (p.sumsq_out != nullptr) *p.sumsq_out = total;
-        if (p.peer_slots != nullptr) {
-            const unsigned long long sq = p.flagged ? seq : p.state->seq;
-            const int g = (int)(sq & (unsigned long long)(kSlotGens - 1));
-            for (int r = 0; r < p.nranks; ++r) slot_publish(p.peer_slots[r], g, p.myrank, total, sq);
+        if (MULTI && p.peer_slots != nullptr) {
+            if (!p.flagged) {  // general decompositions: per-iteration handshake, consumed by pt_finalize_kernel
+                const unsigned long long sq = p.state->seq;
+                const int g = (int)(sq & (unsigned long long)(kSlotGens - 1));
+                for (int r = 0; r < p.nranks; ++r) slot_publish(p.peer_slots[r], g, p.myrank, total, sq);
+            }
         } else if (p.fuse_finalize) {
             pt_finalize(p.state, total, p.err_hist);
         }
     }
-    if (!p.flagged) return;
+    if (!MULTI || !p.flagged) return;
+    // publish this kernel's partial: thread r stores the two words into rank r's mailbox (N posted stores in parallel)
+    __shared__ double total_bc;
+    if (tid == 0) total_bc = total;
+    __syncthreads();
+    if (tid < p.nranks) slot_publish(p.peer_slots[tid], (int)(seq & (unsigned long long)(kSlotGens - 1)), p.myrank, total_bc, seq);
     // lagged evaluation: consume the partials of kernel seq-1 (published a whole kernel ago by every rank)
     __shared__ double vals[kMaxRanks];
     __shared__ int failed;
@@ -369,7 +377,8 @@ struct TmaCfg {
     static constexpr size_t smem_bytes(int S) { return (size_t)S * (A_STRIDE + H_STRIDE) * 8 + (size_t)S * 8 + 128; }
 };
 
-template <int TX, int TY, int S>
+// MULTI = false: the single-slab instantiation (no neighbours, no mailbox): all of the exchange code is compiled out.
+template <int TX, int TY, int S, bool MULTI>
 __global__ void __launch_bounds__((TX / 2) * TY)
     step_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapHt, const StepParams p)
 {
@@ -377,8 +386,10 @@ __global__ void __launch_bounds__((TX / 2) * TY)
     extern __shared__ __align__(128) unsigned char smem_dyn[];  // TMA destinations need 128-byte alignment
     __shared__ double red[32];
     if (p.state != nullptr && p.state->done) return;
-    const unsigned long long seq = p.flagged ? p.state->seq : 0ull;
-    const bool skip = p.flagged && p.state->skip_push;
+    const bool flagged = MULTI && p.flagged;
+    double *const push_lo = MULTI ? p.push_lo : nullptr, *const push_hi = MULTI ? p.push_hi : nullptr;
+    const unsigned long long seq = flagged ? p.state->seq : 0ull;
+    const bool skip = flagged && p.state->skip_push;
 
     // carve-up of the dynamic shared memory (kept in the shared state space: plain LDS/STS, no generic loads)
     double *sA = reinterpret_cast<double *>(smem_dyn);
@@ -387,12 +398,12 @@ __global__ void __launch_bounds__((TX / 2) * TY)
 
     const int tid = threadIdx.x + (TX / 2) * threadIdx.y;
     const int X0 = blockIdx.x * TX, Y0 = blockIdx.y * TY;
-    const int zs = 1 + chunk_of_block(p, blockIdx.z, gridDim.z) * p.zchunk;
+    const int zs = 1 + (MULTI ? chunk_of_block(p, blockIdx.z, gridDim.z) : (int)blockIdx.z) * p.zchunk;
     const int ze = min(zs + p.zchunk, p.nz - 1);
     const int nplanes = (ze - zs) + 2;  // planes zs-1 .. ze
     const int tile = blockIdx.x + gridDim.x * blockIdx.y;
     const bool first_chunk = zs == 1, last_chunk = ze == p.nz - 1;
-    const bool boundary = p.flagged && ((first_chunk && p.push_lo != nullptr) || (last_chunk && p.push_hi != nullptr));
+    const bool boundary = flagged && ((first_chunk && push_lo != nullptr) || (last_chunk && push_hi != nullptr));
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -401,6 +412,27 @@ __global__ void __launch_bounds__((TX / 2) * TY)
         if (boundary) halo_flags_wait(p, tile, first_chunk, last_chunk, seq);
     }
     __syncthreads();
+
+    // Halo push, kept OUT of the plane loop (the loop is the single-slab kernel's, instruction for instruction).
+    // lag-2 (reference) semantics forward the OLD content of Htau2's boundary planes: it is read and stored into the
+    // neighbours right here, before the loop overwrites it -- the planes are on their way within microseconds of the
+    // block's start. Consistent semantics forward the new values: after the loop every thread re-reads the two cells it
+    // has just written (frame cells keep their old content, exactly what the in-loop version forwarded).
+    auto push_planes = [&]() {
+        const int x_ = X0 + 2 * (int)threadIdx.x, y_ = Y0 + (int)threadIdx.y;
+        const bool i0 = x_ < p.nx && y_ < p.ny, i1 = x_ + 1 < p.nx && y_ < p.ny;
+        const size_t pl = (size_t)p.nx * p.ny, o = (size_t)x_ + (size_t)p.nx * y_;
+        if (first_chunk && push_lo != nullptr) {
+            const double *src = p.B + pl;  // plane 1
+            if (i0) push_lo[o] = src[o];
+            if (i1) push_lo[o + 1] = src[o + 1];
+        }
+        if (last_chunk && push_hi != nullptr) {
+            const double *src = p.B + pl * (size_t)(p.nz - 2);
+            if (i0) push_hi[o] = src[o];
+            if (i1) push_hi[o + 1] = src[o + 1];
+        }
+    };
 
     auto issue = [&](int q) {
         const int st = q % S;
@@ -414,6 +446,7 @@ __global__ void __launch_bounds__((TX / 2) * TY)
         const int n0 = nplanes < S ? nplanes : S;
         for (int q = 0; q < n0; ++q) issue(q);
     }
+    if (MULTI && boundary && !p.consistent && !skip) push_planes();  // while the first planes are in flight
 
     const int x = X0 + 2 * (int)threadIdx.x, y = Y0 + (int)threadIdx.y;
     const bool yok = y >= 1 && y <= p.ny - 2;
@@ -456,18 +489,6 @@ __global__ void __launch_bounds__((TX / 2) * TY)
         const double b0 = acur.x - p.dtau * r0;
         const double b1 = acur.y - p.dtau * r1;
         const size_t g = pxy + sz * z;
-
-        const bool plo = p.push_lo != nullptr && z == 1;
-        const bool phi = p.push_hi != nullptr && z == p.nz - 2;
-        double o0 = 0.0, o1 = 0.0;
-        if (plo || phi) {  // block-uniform
-            if (inb0) o0 = p.B[g];
-            if (inb1) o1 = p.B[g + 1];
-            if (p.consistent) {
-                if (valid0) o0 = b0;
-                if (valid1) o1 = b1;
-            }
-        }
         if (valid0 && valid1) {
             *reinterpret_cast<double2 *>(p.B + g) = make_double2(b0, b1);
             if (p.R != nullptr) *reinterpret_cast<double2 *>(p.R + g) = make_double2(r0, r1);
@@ -477,16 +498,15 @@ __global__ void __launch_bounds__((TX / 2) * TY)
         }
         if (valid0) { const double v = r0 * p.norm_scale; acc += v * v; }
         if (valid1) { const double v = r1 * p.norm_scale; acc += v * v; }
-        if (plo && !skip) { if (inb0) p.push_lo[pxy] = o0; if (inb1) p.push_lo[pxy + 1] = o1; }
-        if (phi && !skip) { if (inb0) p.push_hi[pxy] = o0; if (inb1) p.push_hi[pxy + 1] = o1; }
 
         __syncthreads();  // every thread is done with stage stc -> refill it
         if (tid == 0 && q - 1 + S < nplanes) issue(q - 1 + S);
         aprev = acur;
         acur = anext;
     }
+    if (MULTI && boundary && p.consistent) push_planes();
     if (boundary) halo_flags_signal(p, tile, first_chunk, last_chunk, seq, tid);
-    step_epilogue(p, acc, red, seq);
+    step_epilogue<MULTI>(p, acc, red, seq);
 }
 
 // update_halo! of a general Cartesian decomposition (ImplicitGlobalGrid): one plane of `src` (index sp along `axis`) is

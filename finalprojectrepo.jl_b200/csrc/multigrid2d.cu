@@ -801,7 +801,12 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
     // caller's and its upward kernel finishes the cycle). B2S_MG_CLUSTER = 0 disables, 8 / 16 pins the cluster size.
     if (fused_variant_a(*cfg) && !h->coarse_global && h->first_smem >= 2) {
         const char *ec = getenv("B2S_MG_CLUSTER");
-        const int want = (ec && *ec) ? atoi(ec) : 0;  // TODO(measured slower than the per-level kernels so far): off by default
+        // Default: OFF. Measured on B200 (profiles/r02_mid_cluster_*): bit-identical, 13 -> 7 launches, but 0.0813 ms per
+        // 1025^2 V-cycle against 0.0784 with the six small tile kernels -- inside a CUDA graph those cost ~1.85 us each, and a
+        // sweep that exchanges rows between blocks cannot go below ~700 cycles (DSMEM store + mbarrier wake-up + block barrier).
+        const int want = (ec && *ec) ? atoi(ec) : 0;
+        const char *emp = getenv("B2S_MG_CLUSTER_MAXPTS");  // largest level kept in the cluster (larger ones are smem-bandwidth
+        const size_t maxpts = (emp && *emp) ? (size_t)atoll(emp) : (size_t)20000;  // bound on 16 SMs: measured, 257^2 loses)
         const int last = h->first_smem - 1;
         const size_t limit = 200 * 1024;  // + 24 KB of static shared memory (the in-warp coarsest solver's batches) <= 227 KB
         const int tries[2] = {16, 8};
@@ -811,17 +816,19 @@ int b2s_mg_create(b2s_mg **out, const b2s_mg_config *cfg)
             if ((h->ny[last] - 1) % NC != 0 || (h->ny[last] - 1) / NC < 2) continue;
             MidArgs m = {};
             m.base = (h->ny[last] - 1) / NC;
+            const size_t ser0 = (size_t)h->nx[h->first_smem] * h->ny[h->first_smem] * sizeof(double);  // the broadcast correction
             int top = -1;
             for (int cand = last; cand >= 1 && last - cand + 1 <= kMidMaxDist; --cand) {
                 m.ndist = last - cand + 1;
                 for (int l = cand; l <= last; ++l) { m.nx[l - cand] = h->nx[l]; m.ny[l - cand] = h->ny[l]; }
-                if (mid_dist_doubles(m) * sizeof(double) + h->coarse_smem > limit) break;
+                if ((size_t)h->nx[cand] * h->ny[cand] > maxpts) break;
+                if (mid_dist_doubles(m) * sizeof(double) + h->coarse_smem + ser0 > limit) break;
                 top = cand;
             }
             if (top < 0) continue;
             m.ndist = last - top + 1;
             for (int l = top; l <= last; ++l) { m.nx[l - top] = h->nx[l]; m.ny[l - top] = h->ny[l]; }
-            const size_t smem = mid_dist_doubles(m) * sizeof(double) + h->coarse_smem;
+            const size_t smem = mid_dist_doubles(m) * sizeof(double) + h->coarse_smem + ser0;
             MG_CUDA(cudaFuncSetAttribute(mg_mid_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
             if (NC > 8) MG_CUDA(cudaFuncSetAttribute(mg_mid_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             cudaLaunchConfig_t lc = {};

@@ -2305,15 +2305,20 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Thread-block-cluster kernel for the latency-bound middle of the V-cycle (variant A: damped Jacobi + injection).
-// Levels of ~1e3 .. 7e4 points (33^2 .. 257^2 at the 1025^2 bench shape) are chains of dependent sweeps that no amount of
-// SMs speeds up: as separate kernels each level costs two dependent launches (~4 us each, 8 launches = 40 % of the
-// cycle). Here ONE cluster of NC thread blocks keeps those levels in DISTRIBUTED SHARED MEMORY -- every block owns a
-// band of rows of every such level (u, tmp with one halo row on each side, rhs) -- and walks down and up the hierarchy
-// with a cluster barrier (barrier.cluster, ~0.2 us) where a kernel boundary (>= 1.4 us plus the refill of every block's
-// pipeline) used to be. Halo rows are PUSHED: the thread that computes a point of a band's first / last row also stores
-// it into the neighbour block's halo row through the cluster's shared-memory window (st.shared::cluster, no read
-// latency on the critical path); the barrier publishes them. The levels below (<= 17^2) are the one-block chain of
-// mg_coarse_kernel, run by block 0 of the cluster on data the other blocks restricted into its shared memory.
+// Levels of ~1e3 .. 2e4 points (33^2 .. 129^2 at the 1025^2 bench shape) are chains of dependent sweeps that no amount of
+// SMs speeds up: as separate kernels each level costs two dependent launches (~3.5 us each). Here ONE cluster of NC
+// thread blocks keeps those levels in DISTRIBUTED SHARED MEMORY -- every block owns a band of rows of every such level
+// (u, tmp with one halo row on each side, rhs) -- and walks down and up the hierarchy as a DATAFLOW between neighbours:
+//   * a sweep computes the band's first and last row first; the thread that produces such a point also sends it into
+//     the neighbour block's halo row with st.async (shared::cluster store that completes transaction bytes on an mbarrier
+//     in the RECEIVING block: no read latency, no fence, no flag);
+//   * at the end of the sweep every block waits on its own mbarrier for the two rows it is owed (they were sent at the
+//     START of the neighbours' sweep, so the wait is normally over when it begins) -- there is no cluster-wide barrier
+//     after the kernel prologue (measured: barrier.cluster costs ~970 cycles incl. its gpu-scope fence, x18 per cycle);
+//   * write-after-read on a halo row needs no extra synchronisation: a neighbour can only be one sweep ahead, because
+//     its next sweep needs the row this block sends after it has read the halo in question.
+// The levels below (<= 17^2) are the one-block chain of mg_coarse_kernel, run by block 0 on the right-hand side all
+// blocks send into its shared memory; it broadcasts its correction back the same way.
 // Every point is produced by the arithmetic of the unfused kernels: bit-identical results.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMidThreads = 512;
@@ -2328,7 +2333,8 @@ struct MidArgs {
     double *u_out;              // global unknown of level0 (read by the fused upward kernel of the level above)
 };
 
-// shared-memory doubles per block of the distributed levels (every block uses the same offsets)
+// shared-memory doubles per block: bands of the distributed levels + block 0's serial levels + the copy of the first
+// serial level's correction every block receives (every block uses the same offsets)
 __host__ __device__ inline size_t mid_dist_doubles(const MidArgs &m)
 {
     size_t n = 0;
@@ -2339,25 +2345,69 @@ __host__ __device__ inline size_t mid_dist_doubles(const MidArgs &m)
     return n;
 }
 
-// one damped-Jacobi sweep over this block's band [r0, r1) of a level: src/dst have a halo row on each side (local row
-// lr = j - r0 + 1), F has the band only. Points of the first / last band row are also stored into the neighbour's halo
-// row (rem_lo: the lower neighbour's halo row above ITS band; rem_hi: the upper neighbour's halo row 0); nullptr at the ends.
-__device__ __forceinline__ void mid_sweep(const double *__restrict__ src, const double *__restrict__ F, double *__restrict__ dst,
-                                          int nx, int ny, int r0, int r1, const Coef &k, double *rem_lo, double *rem_hi)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank)
 {
-    const int rows = r1 - r0, n = rows * nx;
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+// 8-byte store into another block's shared memory that completes 8 transaction bytes on an mbarrier of THAT block
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr), "d"(v),
+                 "r"(remote_mbar)
+                 : "memory");
+}
+
+struct MidLevelS {
+    int nx, ny, r0, rows, offU, offT, offF, per;
+};
+struct MidSend {  // where a band's first / last row goes: shared::cluster addresses in the neighbour blocks
+    uint32_t lo_addr, lo_bar, hi_addr, hi_bar;
+    bool has_lo, has_hi;
+};
+
+// one damped-Jacobi sweep over this block's band of a level: src/dst have a halo row on each side (local row lr + 1),
+// F has the band only. Band rows are visited first row, last row, then the rest; points of the first / last row are also
+// sent to the neighbours.
+__device__ __forceinline__ void mid_sweep(const double *__restrict__ src, const double *__restrict__ F, double *__restrict__ dst,
+                                          int nx, int ny, int r0, int rows, const Coef &k, const MidSend &sd)
+{
+    const int n = rows * nx;
     for (Idx2 q(threadIdx.x, kMidThreads, nx); q.p < n; q.next()) {
-        const int i = q.i, lr = q.j, j = r0 + lr;
+        const int i = q.i;
+        const int lr = q.j == 0 ? 0 : (q.j == 1 ? rows - 1 : q.j - 1);
+        const int j = r0 + lr;
         const int s = (lr + 1) * nx + i;
         double v = src[s];
         if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
-            const double r = ((src[s + 1] + src[s - 1] + src[s + nx] + src[s - nx] - k.C * v) * k._h2 - F[q.p]);
+            const double r = ((src[s + 1] + src[s - 1] + src[s + nx] + src[s - nx] - k.C * v) * k._h2 - F[lr * nx + i]);
             v = v + k.w * r;
         }
         dst[s] = v;
-        if (lr == 0 && rem_lo != nullptr) rem_lo[i] = v;
-        if (lr == rows - 1 && rem_hi != nullptr) rem_hi[i] = v;
+        if (lr == 0 && sd.has_lo) st_async_f64(sd.lo_addr + 8u * (uint32_t)i, v, sd.lo_bar);
+        if (lr == rows - 1 && sd.has_hi) st_async_f64(sd.hi_addr + 8u * (uint32_t)i, v, sd.hi_bar);
     }
+}
+
+// bilinear prolongation value at fine point (i, j) from a coarse array held with local row crow0 at index 0; the coarse
+// boundary ring counts as 0 (prolong_value_bc with 32-bit indices)
+__device__ __forceinline__ double mid_prolong(const double *__restrict__ ecl, int crow0, int nxc, int nyc, int nx, int i, int j,
+                                              int apply_bcs)
+{
+    if (apply_bcs) {
+        if (i == 0) i = 1;
+        else if (i == nx - 1) i = nx - 2;
+    }
+    const int I = i >> 1, J = j >> 1;
+    const bool io = i & 1, jo = j & 1;
+    auto at = [&](int II, int JJ) -> double {
+        return (II >= 1 && II <= nxc - 2 && JJ >= 1 && JJ <= nyc - 2) ? ecl[(JJ - crow0) * nxc + II] : 0.0;
+    };
+    if (!io && !jo) return at(I, J);
+    if (io && !jo) return 0.5 * at(I, J) + 0.5 * at(I + 1, J);
+    if (!io && jo) return 0.5 * at(I, J) + 0.5 * at(I, J + 1);
+    return ((0.25 * at(I, J) + 0.25 * at(I + 1, J)) + 0.25 * at(I, J + 1)) + 0.25 * at(I + 1, J + 1);
 }
 
 __global__ void __launch_bounds__(kMidThreads) mg_mid_cluster_kernel(const MidArgs m)
@@ -2367,142 +2417,179 @@ __global__ void __launch_bounds__(kMidThreads) mg_mid_cluster_kernel(const MidAr
     extern __shared__ double sm[];
     __shared__ double red[32];
     __shared__ LevelCoef slev[kMaxLevels];
+    __shared__ MidLevelS lv[kMidMaxDist];
+    // [0] / [1]: halo rows of the sweeps that write tmp / u; [2]: block 0 only, the gathered rhs of the first serial level;
+    // [3]: the broadcast correction of the first serial level
+    __shared__ __align__(8) uint64_t bars[4];
     const MGCall *cp = m.ser.cp;
-    if (cp->done) return;  // the same value in every block of the cluster: nobody is left waiting at a barrier
+    if (cp->done) return;  // the same value in every block of the cluster
     const int NC = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
     const double c = cp->c, tol = cp->tol;
     const int apply_bcs = cp->apply_bcs;
     const int nd = m.ndist;
+    const int nxs = m.ser.nx[0], nys = m.ser.ny[0];
     // ---- carve-up (identical offsets in every block) ----------------------------------------------------------
-    double *Ud[kMidMaxDist], *Td[kMidMaxDist], *Fd[kMidMaxDist];
-    int r0[kMidMaxDist], r1[kMidMaxDist], rowsmax[kMidMaxDist];
-    double *ptr = sm;
+    int off = 0;
     for (int d = 0; d < nd; ++d) {
-        const int per = m.base << (nd - 1 - d);
-        rowsmax[d] = per + 1;
-        r0[d] = rank * per;
-        r1[d] = rank == NC - 1 ? m.ny[d] : (rank + 1) * per;
-        Ud[d] = ptr; ptr += (size_t)(rowsmax[d] + 2) * m.nx[d];
-        Td[d] = ptr; ptr += (size_t)(rowsmax[d] + 2) * m.nx[d];
-        Fd[d] = ptr; ptr += (size_t)rowsmax[d] * m.nx[d];
+        const int per = m.base << (nd - 1 - d), rowsmax = per + 1;
+        if (tid == 0) {
+            MidLevelS L;
+            L.nx = m.nx[d]; L.ny = m.ny[d]; L.per = per;
+            L.r0 = rank * per;
+            L.rows = (rank == NC - 1 ? m.ny[d] : (rank + 1) * per) - L.r0;
+            L.offU = off; L.offT = off + (rowsmax + 2) * m.nx[d]; L.offF = off + 2 * (rowsmax + 2) * m.nx[d];
+            lv[d] = L;
+        }
+        off += (2 * (rowsmax + 2) + rowsmax) * m.nx[d];
     }
     double *U[kMaxLevels], *F[kMaxLevels], *T[kMaxLevels];
-    for (int l = 0; l < m.ser.nlev; ++l) {
-        const int n = m.ser.nx[l] * m.ser.ny[l];
-        U[l] = ptr; ptr += n;
-        F[l] = ptr; ptr += n;
-        T[l] = ptr; ptr += n;
-    }
-    U[m.ser.nlev] = ptr;  // CG scratch of the coarsest level
-    // ---- load: constants, rhs band of the first level, u = 0 ------------------------------------------------------
-    if ((int)threadIdx.x < nd + m.ser.nlev) slev[threadIdx.x] = *level_consts(cp, m.level0 + threadIdx.x);
     {
-        const int nx = m.nx[0], rows = r1[0] - r0[0];
-        const double *g = m.rhs_in + (size_t)nx * r0[0];
-        for (int p = threadIdx.x; p < rows * nx; p += kMidThreads) Fd[0][p] = g[p];
-        for (int p = threadIdx.x; p < (rows + 2) * nx; p += kMidThreads) Ud[0][p] = 0.0;
-        if (rank == 0) {
-            const int n = m.ser.nx[0] * m.ser.ny[0];
-            for (int p = threadIdx.x; p < n; p += kMidThreads) U[0][p] = 0.0;
+        double *ptr = sm + off;
+        for (int l = 0; l < m.ser.nlev; ++l) {
+            const int n = m.ser.nx[l] * m.ser.ny[l];
+            U[l] = ptr; ptr += n;
+            F[l] = ptr; ptr += n;
+            T[l] = ptr; ptr += n;
         }
+        U[m.ser.nlev] = ptr;  // CG scratch of the coarsest level (4 x its size)
+        ptr += 4 * m.ser.nx[m.ser.nlev - 1] * m.ser.ny[m.ser.nlev - 1];
+        T[m.ser.nlev] = ptr;  // this block's copy of block 0's correction on the first serial level
     }
-    cluster.sync();  // also: every block of the cluster is running before anyone stores into its shared memory
+    double *Ecopy = T[m.ser.nlev];
+    if (tid < nd + m.ser.nlev) slev[tid] = *level_consts(cp, m.level0 + tid);
+    if (tid == 0) {
+        for (int b_ = 0; b_ < 4; ++b_) mbar_init(&bars[b_], 1);
+        fence_mbar_init();
+        // the two one-shot transfers are armed right away
+        if (rank == 0) mbar_arrive_expect_tx(&bars[2], (uint32_t)(nxs * nys * 8));
+        mbar_arrive_expect_tx(&bars[3], (uint32_t)(nxs * nys * 8));
+    }
+    __syncthreads();
+    // ---- load: rhs band of the first level, u = 0 ------------------------------------------------------------------
+    {
+        const MidLevelS L = lv[0];
+        const double *g = m.rhs_in + (size_t)L.nx * L.r0;
+        double *Fd = sm + L.offF, *Ud = sm + L.offU;
+        for (int p = tid; p < L.rows * L.nx; p += kMidThreads) Fd[p] = g[p];
+        for (int p = tid; p < (L.rows + 2) * L.nx; p += kMidThreads) Ud[p] = 0.0;
+        if (rank == 0)
+            for (int p = tid; p < nxs * nys; p += kMidThreads) U[0][p] = 0.0;
+    }
+    cluster.sync();  // every block of the cluster runs and has initialised its mbarriers before anyone sends to it
     if (rank == 0) {
-        if (m.ser.prof != nullptr && threadIdx.x == 0) m.ser.prof[0] = 0;
+        if (m.ser.prof != nullptr && tid == 0) m.ser.prof[0] = 0;
         coarse_stamp(m.ser);
     }
-    auto coef_of = [&](int l) {
-        Coef k;
-        k.C = slev[l].C; k._h2 = slev[l]._h2; k.w = slev[l].wJ;
-        return k;
-    };
-    // neighbour halo rows of array `a` (one of Ud/Td) of level d
-    auto rem_lo_of = [&](double *a, int d) -> double * {
-        if (rank == 0) return nullptr;
-        const int per = m.base << (nd - 1 - d);  // the lower neighbour is never the last block: its band has `per` rows
-        return cluster.map_shared_rank(a, rank - 1) + (size_t)(per + 1) * m.nx[d];
-    };
-    auto rem_hi_of = [&](double *a, int d) -> double * {
-        if (rank == NC - 1) return nullptr;
-        return cluster.map_shared_rank(a, rank + 1);
-    };
+    uint32_t phase[2] = {0u, 0u};
+    const uint32_t bars_addr = smem_u32(bars), sm_addr = smem_u32(sm);
+    // two sweeps of level d: u -> tmp -> u, halo rows exchanged with the neighbours
     auto two_sweeps = [&](int d) {
-        const Coef k = coef_of(d);
-        mid_sweep(Ud[d], Fd[d], Td[d], m.nx[d], m.ny[d], r0[d], r1[d], k, rem_lo_of(Td[d], d), rem_hi_of(Td[d], d));
-        if (rank == 0) coarse_stamp(m.ser);
-        cluster.sync();
-        if (rank == 0) coarse_stamp(m.ser);
-        mid_sweep(Td[d], Fd[d], Ud[d], m.nx[d], m.ny[d], r0[d], r1[d], k, rem_lo_of(Ud[d], d), rem_hi_of(Ud[d], d));
-        if (rank == 0) coarse_stamp(m.ser);
-        cluster.sync();
-        if (rank == 0) coarse_stamp(m.ser);
+        const MidLevelS L = lv[d];
+        Coef k;
+        k.C = slev[d].C; k._h2 = slev[d]._h2; k.w = slev[d].wJ;
+        double *Ud = sm + L.offU, *Td = sm + L.offT;
+        const double *Fd = sm + L.offF;
+        const bool has_lo = rank > 0, has_hi = rank < NC - 1;
+        const uint32_t bytes = (uint32_t)((has_lo ? 1 : 0) + (has_hi ? 1 : 0)) * (uint32_t)L.nx * 8u;
+#pragma unroll
+        for (int sw = 0; sw < 2; ++sw) {
+            const int dstoff = sw == 0 ? L.offT : L.offU;
+            MidSend sd;
+            sd.has_lo = has_lo; sd.has_hi = has_hi;
+            // my first row -> the lower neighbour's halo row above its band (its band has `per` rows: it is never the last block)
+            sd.lo_addr = has_lo ? mapa_u32(sm_addr + 8u * (uint32_t)(dstoff + (L.per + 1) * L.nx), (uint32_t)(rank - 1)) : 0u;
+            sd.lo_bar = has_lo ? mapa_u32(bars_addr + 8u * (uint32_t)sw, (uint32_t)(rank - 1)) : 0u;
+            // my last row -> the upper neighbour's halo row 0
+            sd.hi_addr = has_hi ? mapa_u32(sm_addr + 8u * (uint32_t)dstoff, (uint32_t)(rank + 1)) : 0u;
+            sd.hi_bar = has_hi ? mapa_u32(bars_addr + 8u * (uint32_t)sw, (uint32_t)(rank + 1)) : 0u;
+            if (tid == 0 && bytes != 0u) mbar_arrive_expect_tx(&bars[sw], bytes);
+            mid_sweep(sw == 0 ? Ud : Td, Fd, sw == 0 ? Td : Ud, L.nx, L.ny, L.r0, L.rows, k, sd);
+            if (bytes != 0u) {
+                mbar_wait(&bars[sw], phase[sw]);
+                phase[sw] ^= 1u;
+            }
+            __syncthreads();
+            if (rank == 0) coarse_stamp(m.ser);
+        }
     };
-    // injected residual of the smoothed u at coarse point (I, J) of level d+1, from this block's band of level d
-    auto coarse_rhs = [&](int d, int I, int J, int nxc, int nyc, const Coef &k) -> double {
+    // injected residual of the smoothed u at coarse point (I, J) of the next level, from this block's band of level d
+    auto coarse_rhs = [&](const MidLevelS &L, const Coef &k, int I, int J, int nxc, int nyc) -> double {
         if (apply_bcs) {
             if (I == 0) I = 1;
             else if (I == nxc - 1) I = nxc - 2;
         }
         if (I < 1 || I > nxc - 2 || J < 1 || J > nyc - 2) return 0.0;
-        const int nx = m.nx[d];
-        const int s = (2 * J - r0[d] + 1) * nx + 2 * I;
-        const double *u = Ud[d];
-        return ((u[s + 1] + u[s - 1] + u[s + nx] + u[s - nx] - k.C * u[s]) * k._h2 - Fd[d][(2 * J - r0[d]) * nx + 2 * I]);
+        const int nx = L.nx;
+        const int s = (2 * J - L.r0 + 1) * nx + 2 * I;
+        const double *u = sm + L.offU;
+        return ((u[s + 1] + u[s - 1] + u[s + nx] + u[s - nx] - k.C * u[s]) * k._h2 - sm[L.offF + (2 * J - L.r0) * nx + 2 * I]);
     };
     // ---- downward leg over the distributed levels -----------------------------------------------------------------
     for (int d = 0; d < nd; ++d) {
         two_sweeps(d);
-        const Coef k = coef_of(d);
+        const MidLevelS L = lv[d];
+        Coef k;
+        k.C = slev[d].C; k._h2 = slev[d]._h2; k.w = slev[d].wJ;
         if (d + 1 < nd) {
-            const int nxc = m.nx[d + 1], nyc = m.ny[d + 1], c0 = r0[d + 1], rowsc = r1[d + 1] - r0[d + 1];
-            for (Idx2 q(threadIdx.x, kMidThreads, nxc); q.p < rowsc * nxc; q.next())
-                Fd[d + 1][q.p] = coarse_rhs(d, q.i, c0 + q.j, nxc, nyc, k);
-            for (int p = threadIdx.x; p < (rowsc + 2) * nxc; p += kMidThreads) Ud[d + 1][p] = 0.0;
+            const MidLevelS Lc = lv[d + 1];
+            double *Fc = sm + Lc.offF, *Uc = sm + Lc.offU;
+            for (Idx2 q(tid, kMidThreads, Lc.nx); q.p < Lc.rows * Lc.nx; q.next())
+                Fc[q.p] = coarse_rhs(L, k, q.i, Lc.r0 + q.j, Lc.nx, Lc.ny);
+            for (int p = tid; p < (Lc.rows + 2) * Lc.nx; p += kMidThreads) Uc[p] = 0.0;
             __syncthreads();
-            if (rank == 0) coarse_stamp(m.ser);
-        } else {  // into block 0's copy of the first serial level
-            const int nxc = m.ser.nx[0], nyc = m.ser.ny[0];
-            const int c0 = r0[d] >> 1, c1 = rank == NC - 1 ? nyc : (r1[d] >> 1);
-            double *F0 = cluster.map_shared_rank(F[0], 0);
-            for (Idx2 q(threadIdx.x, kMidThreads, nxc); q.p < (c1 - c0) * nxc; q.next())
-                F0[(c0 + q.j) * nxc + q.i] = coarse_rhs(d, q.i, c0 + q.j, nxc, nyc, k);
-            cluster.sync();
+        } else {  // into block 0's copy of the first serial level: every block sends its rows (block 0 included)
+            const int c0 = L.r0 >> 1, c1 = rank == NC - 1 ? nys : ((L.r0 + L.rows) >> 1);
+            const uint32_t f0 = mapa_u32(smem_u32(F[0]), 0u), b2 = mapa_u32(bars_addr + 16u, 0u);
+            for (Idx2 q(tid, kMidThreads, nxs); q.p < (c1 - c0) * nxs; q.next())
+                st_async_f64(f0 + 8u * (uint32_t)((c0 + q.j) * nxs + q.i), coarse_rhs(L, k, q.i, c0 + q.j, nxs, nys), b2);
+        }
+        if (rank == 0) coarse_stamp(m.ser);
+    }
+    // ---- the serial tail in block 0, its correction broadcast to every block ---------------------------------------
+    if (rank == 0) {
+        mbar_wait(&bars[2], 0u);
+        __syncthreads();
+        coarse_chain(m.ser, U, F, T, slev + nd, red, c, tol, apply_bcs, false);
+        for (int p = tid; p < nxs * nys; p += kMidThreads) {
+            const double v = U[0][p];
+            for (int r = 0; r < NC; ++r)
+                st_async_f64(mapa_u32(smem_u32(Ecopy) + 8u * (uint32_t)p, (uint32_t)r), v, mapa_u32(bars_addr + 24u, (uint32_t)r));
         }
     }
-    // ---- the serial tail in block 0 ------------------------------------------------------------------------------------
-    if (rank == 0) coarse_stamp(m.ser);
-    if (rank == 0) coarse_chain(m.ser, U, F, T, slev + nd, red, c, tol, apply_bcs, false);
-    cluster.sync();
+    mbar_wait(&bars[3], 0u);
+    __syncthreads();
     if (rank == 0) coarse_stamp(m.ser);
     // ---- upward leg ------------------------------------------------------------------------------------------------------
     for (int d = nd - 1; d >= 0; --d) {
-        const int nx = m.nx[d], ny = m.ny[d];
-        int nxc, nyc;
-        const double *ecb;  // coarse correction, indexable with GLOBAL coarse rows
+        const MidLevelS L = lv[d];
+        const double *ecl;
+        int crow0, nxc, nyc;
         if (d + 1 < nd) {
-            nxc = m.nx[d + 1]; nyc = m.ny[d + 1];
-            ecb = Ud[d + 1] - (ptrdiff_t)(r0[d + 1] - 1) * nxc;
+            const MidLevelS Lc = lv[d + 1];
+            ecl = sm + Lc.offU; crow0 = Lc.r0 - 1; nxc = Lc.nx; nyc = Lc.ny;
         } else {
-            nxc = m.ser.nx[0]; nyc = m.ser.ny[0];
-            ecb = cluster.map_shared_rank(U[0], 0);
+            ecl = Ecopy; crow0 = 0; nxc = nxs; nyc = nys;
         }
         // u -= P(e) on the band and on its two halo rows (their coarse neighbours are in the coarse band's halo rows)
-        const int jlo = rank == 0 ? r0[d] : r0[d] - 1, jhi = rank == NC - 1 ? r1[d] : r1[d] + 1;
-        for (Idx2 q(threadIdx.x, kMidThreads, nx); q.p < (jhi - jlo) * nx; q.next()) {
+        const int jlo = rank == 0 ? L.r0 : L.r0 - 1, jhi = rank == NC - 1 ? L.r0 + L.rows : L.r0 + L.rows + 1;
+        double *Ud = sm + L.offU;
+        for (Idx2 q(tid, kMidThreads, L.nx); q.p < (jhi - jlo) * L.nx; q.next()) {
             const int j = jlo + q.j;
-            const int s = (j - r0[d] + 1) * nx + q.i;
-            Ud[d][s] = Ud[d][s] - prolong_value_bc(ecb, nxc, nyc, nx, q.i, j, apply_bcs);
+            const int s = (j - L.r0 + 1) * L.nx + q.i;
+            Ud[s] = Ud[s] - mid_prolong(ecl, crow0, nxc, nyc, L.nx, q.i, j, apply_bcs);
         }
         __syncthreads();
         if (rank == 0) coarse_stamp(m.ser);
         two_sweeps(d);
     }
     {
-        const int nx = m.nx[0], rows = r1[0] - r0[0];
-        double *g = m.u_out + (size_t)nx * r0[0];
-        const double *u = Ud[0] + nx;
-        for (int p = threadIdx.x; p < rows * nx; p += kMidThreads) g[p] = u[p];
+        const MidLevelS L = lv[0];
+        double *g = m.u_out + (size_t)L.nx * L.r0;
+        const double *u = sm + L.offU + L.nx;
+        for (int p = tid; p < L.rows * L.nx; p += kMidThreads) g[p] = u[p];
     }
+    // every block has waited for everything that was sent to it: nobody's shared memory is written after it exits
 }
 
 // tol_rhs = tol * sqrt(sum(rhs.^2)/(nx*ny)) and the exit threshold of a global-memory coarsest Jacobi solve
