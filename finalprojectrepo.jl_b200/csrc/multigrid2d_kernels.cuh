@@ -997,8 +997,18 @@ __global__ void __launch_bounds__(kSNT, B2S_STREAM_MINBLOCKS) mg_up_stream_kerne
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kS2NT = 128;
 constexpr int kS2W = 2 * kS2NT - 8;   // output columns per strip
-constexpr int kS2D = 6, kS2Ring = 8;  // bulk-copy prefetch depth (<= ring - 2) / ring rows (= unroll factor, multiple of 4)
-constexpr int kS2DC = 4;              // look-ahead of the coarse rows (cp.async groups), <= 2 * kS2CRing - 4
+#ifndef B2S_S2_RING
+#define B2S_S2_RING 8
+#endif
+#ifndef B2S_S2_D
+#define B2S_S2_D (B2S_S2_RING - 2)
+#endif
+#ifndef B2S_S2_DC
+#define B2S_S2_DC (B2S_S2_RING - 4)
+#endif
+constexpr int kS2D = B2S_S2_D, kS2Ring = B2S_S2_RING;  // bulk-copy prefetch depth (<= ring - 2) / ring rows (= unroll factor, multiple of 4)
+constexpr int kS2DC = B2S_S2_DC;      // look-ahead of the coarse rows (cp.async groups), <= 2 * kS2CRing - 4
+static_assert(kS2Ring % 4 == 0 && kS2D <= kS2Ring - 2 && kS2DC <= kS2Ring - 4 && kS2DC >= 1, "stream2 ring parameters");
 constexpr int kS2CRing = kS2Ring / 2;
 constexpr int kS2P = 2 * kS2NT + 4;   // ring pitch: 2 pad elements left, parity shift, right pad (even)
 constexpr int kS2CW = kS2NT + 2;      // coarse window width
