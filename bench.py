@@ -129,18 +129,43 @@ def host_threads():
 
 
 def bind_to_gpu_numa_node(index):
-    """Pin this process (and therefore the pinned host buffers it is about to allocate, first touch) to the CPUs of the
-    NUMA node the GPU hangs off: with 8 unbound ranks the staging traffic of all GPUs crosses one socket."""
+    """Before the pinned host buffers of this rank are allocated: prefer the memory of the NUMA node the GPU hangs off
+    (set_mempolicy(MPOL_PREFERRED) -- works even when the container's cpuset covers one socket only) and, where the
+    cpuset allows it, run on that node's CPUs. With 8 unbound ranks the staging traffic of all GPUs crosses one socket."""
+    info = {"gpu": index}
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        before = len(os.sched_getaffinity(0))
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        after = sorted(os.sched_getaffinity(0))
-        return {"gpu": index, "cpus_before": before, "cpus": len(after), "first_cpu": after[0], "last_cpu": after[-1]}
+        import ctypes
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+        node = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pci = pynvml.nvmlDeviceGetPciInfo(h)
+            busid = pci.busId.decode() if isinstance(pci.busId, bytes) else pci.busId
+            path = "/sys/bus/pci/devices/" + busid.lower()[-12:] + "/numa_node"
+            node = int(open(path).read().strip())
+            info["pci"] = busid
+            try:
+                before = len(os.sched_getaffinity(0))
+                pynvml.nvmlDeviceSetCpuAffinity(h)
+                info["cpus"] = [before, len(os.sched_getaffinity(0))]
+            except Exception as e:  # noqa: BLE001
+                info["cpu_affinity"] = f"{type(e).__name__}"
+        except Exception as e:  # noqa: BLE001
+            info["nvml"] = f"{type(e).__name__}: {e}"
+        info["numa_node"] = node
+        if node is not None and node >= 0:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86_64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["set_mempolicy"] = "ok" if rc == 0 else f"errno {ctypes.get_errno()}"
+        del bus
     except Exception as e:  # noqa: BLE001
-        return {"gpu": index, "unavailable": f"{type(e).__name__}: {e}"}
+        info["unavailable"] = f"{type(e).__name__}: {e}"
+    return info
 
 
 def cpu_reference_run(n, seconds, threads=None):

@@ -268,6 +268,13 @@ struct b2s_diff3d {
     double last_ms = 0.0;
     PTState *pinned = nullptr;    // host staging of the state: [0] upload, [1], [2] polled snapshots
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+    // small (L2-resident) grids on one device: a whole batch of PT iterations is one CUDA graph per ping-pong parity (a
+    // kernel boundary inside a graph costs ~1.4 us, a stream launch ~2.3 us of device-side gap: at 32^3..128^3 that is
+    // 15-50 % of an iteration). The kernels' arguments never change, so the graphs are built once per handle.
+    bool use_graph = false, warmed = false;
+    int graph_batch = 0;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    long long graph_launches_per_batch = 0;
     int it_step = 0;              // iter_inner of the time step in progress
 };
 
@@ -524,6 +531,7 @@ int run_loop(b2s_diff3d *h, PTState st, PTState *out)
         batch = cells >= 256.0 * 256 * 256 ? 16 : (cells >= 96.0 * 96 * 96 ? 64 : 128);
         if (!st.check) batch = 512;  // fixed count: nothing to poll for but errors
     }
+    if (h->use_graph) batch = h->graph_batch;
     DeviceCtx &d0 = h->devs[0];
     PTState *src = h->zstack ? h->slabs[0].state : d0.state;
     PTState cur = st;
@@ -531,7 +539,31 @@ int run_loop(b2s_diff3d *h, PTState st, PTState *out)
     auto submit = [&]() -> int {
         const int n = std::min(batch, st.iter_max - st.it - enqueued);
         if (n <= 0) return B2S_OK;
-        for (int i = 0; i < n; ++i) B2S_CHECK(launch_iteration(h));
+        if (h->use_graph && n == h->graph_batch && h->warmed) {  // (the very first batch runs as stream launches: it
+                                                                   // sets the kernels' shared-memory attributes)
+            const int par = (int)(h->launched & 1);
+            if (!h->graph[par]) {  // capture n iterations starting at this parity (nothing executes during the capture)
+                const long long launched0 = h->launched, kl0 = h->kernel_launches;
+                cudaGraph_t g = nullptr;
+                B2S_CUDA(cudaSetDevice(d0.dev));
+                B2S_CUDA(cudaStreamBeginCapture(d0.stream, cudaStreamCaptureModeThreadLocal));
+                int rc = B2S_OK;
+                for (int i = 0; i < n && rc == B2S_OK; ++i) rc = launch_iteration(h);
+                cudaError_t e = cudaStreamEndCapture(d0.stream, &g);
+                h->graph_launches_per_batch = h->kernel_launches - kl0;
+                h->launched = launched0; h->kernel_launches = kl0;
+                if (rc != B2S_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                B2S_CUDA(e);
+                B2S_CUDA(cudaGraphInstantiate(&h->graph[par], g, 0));
+                B2S_CUDA(cudaGraphDestroy(g));
+            }
+            B2S_CUDA(cudaGraphLaunch(h->graph[par], d0.stream));
+            h->launched += n;
+            h->kernel_launches += h->graph_launches_per_batch;
+        } else {
+            for (int i = 0; i < n; ++i) B2S_CHECK(launch_iteration(h));
+            h->warmed = true;
+        }
         if (h->zstack) B2S_CHECK(enqueue_lagged_finalize(h));
         B2S_CUDA(cudaSetDevice(d0.dev));
         B2S_CUDA(cudaMemcpyAsync(h->pinned + 1 + slot, src, sizeof(PTState), cudaMemcpyDeviceToHost, d0.stream));
@@ -578,6 +610,8 @@ int ensure_hist(b2s_diff3d *h, int n)
         d.err_hist = nullptr;
         B2S_CUDA(cudaMalloc(&d.err_hist, sizeof(double) * (size_t)n));
         d.err_hist_cap = n;
+        for (int i = 0; i < 2; ++i)  // the captured launches carry the old history pointer
+            if (h->graph[i]) { cudaGraphExecDestroy(h->graph[i]); h->graph[i] = nullptr; }
     }
     return B2S_OK;
 }
@@ -626,8 +660,10 @@ int destroy_impl(b2s_diff3d *h)
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     if (!h->devs.empty()) cudaSetDevice(h->devs[0].dev);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
         if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
+        if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+    }
     for (Slab &s : h->slabs) {
         cudaSetDevice(s.dev);
         if (s.arena) cudaFree(s.arena);
@@ -792,6 +828,13 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
             }
             h->nblocks = tiles * ((cfg->nz - 2 + h->zchunk - 1) / h->zchunk);
         }
+    }
+    // batches of iterations as CUDA graphs: one device, no cross-device events in the iteration, L2-resident grid
+    {
+        const int eg = env_int("B2S_DIFF_GRAPH", -1);
+        const double cells = (double)h->ar.cells * (double)h->slabs.size();
+        h->use_graph = h->devs.size() == 1 && !h->cart && (eg < 0 ? cells <= 200.0 * 200 * 200 : eg != 0);
+        h->graph_batch = cfg->batch > 0 ? cfg->batch : ((double)h->ar.cells >= 256.0 * 256 * 256 ? 16 : ((double)h->ar.cells >= 96.0 * 96 * 96 ? 64 : 128));
     }
     // in-process neighbours and partial-sum destinations
     if (cfg->slab_count == cfg->nslabs_total) {
