@@ -106,6 +106,13 @@ static int pick_zchunk(int nxy_tiles, int nz, int max_blocks)
     if (nxy_tiles > max_blocks) return 0;
     int zc = env_int("B2S_ZCHUNK", 0);
     const int interior = nz - 2;
+    if (zc <= 0 && (long long)nxy_tiles * interior <= 6000) {
+        // L2-resident grids (up to ~128^3) are latency-bound: a block's time is its chain of dependent planes, so short
+        // chunks win as long as there are not many more blocks than ~700 (measured on B200, profiles/r02_small_grid_zchunk.jsonl:
+        // 32^3 10.9 -> 6.3 us, 64^3 8.5 -> 6.5 us, 128^3 13.3 -> 12.8 us per iteration)
+        const int chunks = std::max(1, (700 + nxy_tiles - 1) / nxy_tiles);
+        zc = std::max(2, (interior + chunks - 1) / chunks);
+    }
     if (zc <= 0) {
         const int want_blocks = 148 * 8;
         int chunks = (want_blocks + nxy_tiles - 1) / nxy_tiles;
@@ -257,6 +264,7 @@ struct b2s_diff3d {
     bool multi = false;           // more than one slab in the global stack
     bool cart = false;            // decomposition in x or y as well: update_halo! as separate plane copies
     bool zstack = false;          // multi && !cart: fused halo push with neighbour flags, lagged norm evaluation
+    bool cart_devbarrier = false; // in-process general decomposition with one rank per device: device-side rank barriers
     int ntiles = 0;               // xy tiles per launch (= halo flags per array)
     int skip_push = 0;            // host mirror of PTState::skip_push
     std::vector<char *> peer_base; // one process per GPU: every rank's arena (own or IPC-mapped), in rank order
@@ -377,9 +385,64 @@ int cart_update_halo_multiprocess(b2s_diff3d *h, int which)
     return B2S_OK;
 }
 
+// In-process handle whose ranks all sit on DIFFERENT devices: the same pull + device-side rank barrier as with one process
+// per GPU (every device runs its own stream; the barrier kernels of different devices run concurrently, so they may wait
+// on one another). The event-based version below costs 4 x (N records + N(N-1) stream waits) host calls and as many
+// cross-device event latencies per iteration (measured: 584 us per iteration for the 2x2x2 grid on 8 GPUs).
+int cart_update_halo_devbarrier(b2s_diff3d *h, int which)
+{
+    const b2s_diff3d_config &c = h->cfg;
+    int dims[3];
+    cart_dims(c, dims);
+    const int nd[3] = {c.nx, c.ny, c.nz};
+    int k = 1;
+    auto barrier_all = [&]() -> int {
+        for (Slab &me : h->slabs) {
+            DeviceCtx &d = h->devs[me.devslot];
+            B2S_CUDA(cudaSetDevice(me.dev));
+            cart_barrier_kernel<<<1, kMaxRanks, 0, d.stream>>>(d.state, (CartSync *)(me.arena + h->ar.off_cart),
+                                                               (CartSync *const *)(me.arena + h->ar.off_cart_table), c.nslabs_total,
+                                                               me.rank, k, (long long)20e9);
+            h->kernel_launches += 1;
+        }
+        ++k;
+        return B2S_OK;
+    };
+    B2S_CHECK(barrier_all());  // every rank's step kernel is done before anyone's halo cells change
+    for (int axis = 0; axis < 3; ++axis) {
+        if (dims[axis] == 1) continue;
+        const size_t plane = (size_t)nd[(axis + 1) % 3] * nd[(axis + 2) % 3];
+        const int blocks = (int)std::min<size_t>((plane + 255) / 256, 592);
+        const int n = nd[axis];
+        for (Slab &me : h->slabs) {
+            DeviceCtx &d = h->devs[me.devslot];
+            int coord[3];
+            cart_coords(c, me.rank, coord);
+            B2S_CUDA(cudaSetDevice(me.dev));
+            auto nb_buf = [&](int delta) {
+                int cc[3] = {coord[0], coord[1], coord[2]};
+                cc[axis] += delta;
+                return h->slabs[(size_t)((cc[0] * dims[1] + cc[1]) * dims[2] + cc[2])].buf[which];
+            };
+            if (coord[axis] > 0) {  // low neighbour's plane n-2 -> my plane 0
+                halo_plane_copy_kernel<<<blocks, 256, 0, d.stream>>>(nb_buf(-1), me.buf[which], axis, n - 2, 0, c.nx, c.ny, c.nz, d.state);
+                h->kernel_launches += 1;
+            }
+            if (coord[axis] + 1 < dims[axis]) {  // high neighbour's plane 1 -> my plane n-1
+                halo_plane_copy_kernel<<<blocks, 256, 0, d.stream>>>(nb_buf(+1), me.buf[which], axis, 1, n - 1, c.nx, c.ny, c.nz, d.state);
+                h->kernel_launches += 1;
+            }
+        }
+        B2S_CHECK(barrier_all());  // the next axis (or the next step kernel) touches cells this one has read or written
+    }
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+}
+
 int cart_update_halo(b2s_diff3d *h, int which)
 {
     if (h->slabs.size() == 1 && h->multi) return cart_update_halo_multiprocess(h, which);
+    if (h->cart_devbarrier) return cart_update_halo_devbarrier(h, which);
     const b2s_diff3d_config &c = h->cfg;
     int dims[3];
     cart_dims(c, dims);
@@ -873,6 +936,16 @@ int b2s_diff3d_create(b2s_diff3d **out, const b2s_diff3d_config *cfg)
             for (DeviceCtx &d : h->devs) {
                 CUDA_FAIL_IF(cudaSetDevice(d.dev));
                 CUDA_FAIL_IF(cudaEventCreateWithFlags(&d.ev_bar, cudaEventDisableTiming));
+            }
+            // one rank per device: phase mailboxes of all ranks, reachable through peer access
+            h->cart_devbarrier = h->slabs.size() > 1 && h->devs.size() == h->slabs.size() && env_int("B2S_CART_EVENTS", 0) == 0;
+            if (h->cart_devbarrier) {
+                std::vector<CartSync *> ct;
+                for (Slab &s : h->slabs) ct.push_back((CartSync *)(s.arena + h->ar.off_cart));
+                for (Slab &s : h->slabs) {
+                    CUDA_FAIL_IF(cudaSetDevice(s.dev));
+                    CUDA_FAIL_IF(cudaMemcpy(s.arena + h->ar.off_cart_table, ct.data(), sizeof(CartSync *) * ct.size(), cudaMemcpyHostToDevice));
+                }
             }
         }
         if (h->cart) {
