@@ -1050,6 +1050,39 @@ __device__ __forceinline__ double2 ld_pair(const double *row, int ci)
     return make_double2(row[ci + 1], row[ci + 2]);
 }
 
+// x neighbours of a thread's column pair in the two-column streaming kernels: the left neighbour column is the SECOND
+// column of thread t-1, the right one the FIRST column of thread t+1 -- both live in the neighbour lanes' registers, so
+// they travel by warp shuffle; only the first / last lane of a warp reads the shared-memory ring row (where the edge
+// lanes of the neighbouring warps published their pairs). The stride-2 8-byte ring loads this replaces were 2-way bank
+// conflicts (ncu r02: 30-38 % of the streaming kernels' shared-memory wavefronts).
+// MEASURED SLOWER and therefore OFF by default (profiles/r02_stream2_shuffle_ab.jsonl: 4097^2 0.372 vs 0.326 ms per V-cycle,
+// bit-identical): the kernels are bound by the per-row dependency chain, not by shared-memory bandwidth, and a 64-bit
+// shuffle (25 cycles, two SHFL) plus the predicated edge load is a longer link in that chain than the conflicted LDS.64.
+#ifndef B2S_S2_SHFL
+#define B2S_S2_SHFL 0
+#endif
+__device__ __forceinline__ void pair_neighbours(const double2 &v, const double *ring_row, int ci, int lane, double &xl, double &xr)
+{
+#if B2S_S2_SHFL
+    xl = __shfl_up_sync(0xffffffffu, v.y, 1);
+    xr = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (lane == 0) xl = ring_row[ci - 1];
+    if (lane == 31) xr = ring_row[ci + 2];
+#else
+    xl = ring_row[ci - 1];
+    xr = ring_row[ci + 2];
+#endif
+}
+// publish a pair in a ring row for the neighbouring warps' edge lanes (every lane when the shuffle path is disabled)
+__device__ __forceinline__ void publish_pair(double *ring_row, int ci, int lane, const double2 &v)
+{
+#if B2S_S2_SHFL
+    if (lane == 0 || lane == 31) *reinterpret_cast<double2 *>(ring_row + ci) = v;
+#else
+    *reinterpret_cast<double2 *>(ring_row + ci) = v;
+#endif
+}
+
 __device__ __forceinline__ double jac_res(double xp, double xm, double yp, double ym, double c, double f, const Coef &k)
 {
     return ((xp + xm + yp + ym - k.C * c) * k._h2 - f);
@@ -1108,6 +1141,7 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_down_stream2_kernel(const TileA
         }
     }
     __syncthreads();
+    const int lane = t & 31;
     const int Ic = x0 >> 1;  // x0 is even: the coarse column this thread writes on even rows
     const bool cint = Ic >= 1 && Ic <= nxc - 2;
     const bool cmir_lo = apply_bcs && Ic == 1, cmir_hi = apply_bcs && Ic == nxc - 2;
@@ -1133,23 +1167,32 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_down_stream2_kernel(const TileA
             double2 p_c = u_b;
             if ((unsigned)(ya - 1) < (unsigned)(ny - 2)) {
                 const double *row = U0 + ((j + kS2Ring - 1) % kS2Ring) * kS2P + (j & 1);
-                const double xl = row[ci - 1], xr = row[ci + 2];
+                double xl, xr;
+                pair_neighbours(u_b, row, ci, lane, xl, xr);
                 if (i0) p_c.x = u_b.x + k.w * jac_res(u_b.y, xl, u_c.x, u_a.x, u_b.x, f_c.x, k);
                 if (i1) p_c.y = u_b.y + k.w * jac_res(xr, u_b.x, u_c.y, u_a.y, u_b.y, f_c.y, k);
             }
-            *reinterpret_cast<double2 *>(S1 + ((j + 3) & 3) * kS2P + ci) = p_c;
+            publish_pair(S1 + ((j + 3) & 3) * kS2P, ci, lane, p_c);
             // stage B: second sweep at row s-2
             const int yb = s - 2;
             double2 q_c = p_b;
             if ((unsigned)(yb - 1) < (unsigned)(ny - 2)) {
                 const double *row = S1 + ((j + 2) & 3) * kS2P;
-                const double xl = row[ci - 1], xr = row[ci + 2];
+                double xl, xr;
+                pair_neighbours(p_b, row, ci, lane, xl, xr);
                 if (i0) q_c.x = p_b.x + k.w * jac_res(p_b.y, xl, p_c.x, p_a.x, p_b.x, f_b.x, k);
                 if (i1) q_c.y = p_b.y + k.w * jac_res(xr, p_b.x, p_c.y, p_a.y, p_b.y, f_b.y, k);
             }
-            *reinterpret_cast<double2 *>(S2 + ((j + 2) & 3) * kS2P + ci) = q_c;
+            publish_pair(S2 + ((j + 2) & 3) * kS2P, ci, lane, q_c);
             // stage C: output row s-3
             const int yc = s - 3;
+#if B2S_S2_SHFL
+            double xl_q = 0.0;  // left neighbour of q_b's first column (needed on even rows only: compile-time)
+            if ((j & 1) == 0) {
+                xl_q = __shfl_up_sync(0xffffffffu, q_b.y, 1);
+                if (lane == 0) xl_q = S2[((j + 1) & 3) * kS2P + ci - 1];
+            }
+#endif
             if ((unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
                 const size_t g = (size_t)x0 + (size_t)nx * yc;
                 if (o0) a.u_out[g] = q_b.x;
@@ -1160,7 +1203,11 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_down_stream2_kernel(const TileA
                     a.ec[pc] = 0.0;
                     const bool jint = (unsigned)(J - 1) < (unsigned)(nyc - 2);
                     if (cint && jint) {
+#if B2S_S2_SHFL
+                        const double xl = xl_q;
+#else
                         const double xl = S2[((j + 1) & 3) * kS2P + ci - 1];
+#endif
                         const double v = jac_res(q_b.y, xl, q_c.x, q_a.x, q_b.x, f_a.x, k);
                         a.rc[pc] = v;
                         if (cmir_lo) a.rc[(size_t)0 + (size_t)nxc * J] = v;
@@ -1208,6 +1255,7 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
     const bool bc_first = apply_bcs && x0 == 0;       // fine[0,:] = fine[1,:]
     const bool bc_last = apply_bcs && x0 == nx - 1;   // fine[nx-1,:] = fine[nx-2,:]
     const bool producer = threadIdx.x >= kS2NT;  // see mg_down_stream2_kernel
+    const int lane = t & 31;
     if (threadIdx.x == kS2NT) {
         for (int r = 0; r < kS2Ring; ++r) mbar_init(&bars[r], 1);
         fence_mbar_init();
@@ -1282,24 +1330,26 @@ __global__ void __launch_bounds__(kS2NT + 32) mg_up_stream2_kernel(const TileArg
                 if (bc_first) e0 = e1;
             }
             const double2 c_c = make_double2(us.x - e0, us.y - e1);
-            *reinterpret_cast<double2 *>(C0 + (j & 3) * kS2P + ci) = c_c;
+            publish_pair(C0 + (j & 3) * kS2P, ci, lane, c_c);
             // stage B: first post-sweep at row s-1
             const int yb = s - 1;
             double2 t_c = c_b;
             if ((unsigned)(yb - 1) < (unsigned)(ny - 2)) {
                 const double *row = C0 + ((j + 3) & 3) * kS2P;
-                const double xl = row[ci - 1], xr = row[ci + 2];
+                double xl, xr;
+                pair_neighbours(c_b, row, ci, lane, xl, xr);
                 if (i0) t_c.x = c_b.x + k.w * jac_res(c_b.y, xl, c_c.x, c_a.x, c_b.x, f_b.x, k);
                 if (i1) t_c.y = c_b.y + k.w * jac_res(xr, c_b.x, c_c.y, c_a.y, c_b.y, f_b.y, k);
             }
-            *reinterpret_cast<double2 *>(T1 + ((j + 3) & 3) * kS2P + ci) = t_c;
+            publish_pair(T1 + ((j + 3) & 3) * kS2P, ci, lane, t_c);
             // stage C: second post-sweep at row s-2 -> u, sum of its pre-update res^2
             const int yc = s - 2;
             if ((unsigned)(yc - Y0) < (unsigned)(Y1 - Y0)) {
                 double2 v = t_b;
                 if ((unsigned)(yc - 1) < (unsigned)(ny - 2)) {
                     const double *row = T1 + ((j + 2) & 3) * kS2P;
-                    const double xl = row[ci - 1], xr = row[ci + 2];
+                    double xl, xr;
+                    pair_neighbours(t_b, row, ci, lane, xl, xr);
                     if (i0 && o0) {
                         const double res = jac_res(t_b.y, xl, t_c.x, t_a.x, t_b.x, f_a.x, k);
                         acc += res * res;
