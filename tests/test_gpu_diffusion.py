@@ -422,3 +422,23 @@ def test_x_g_covers_the_rank_grid_and_thin_grids_are_rejected(b2s, gpu):
     with pytest.raises(capi.B2SError) as ei:
         part1.Diffusion3D(4097, 4100, 3)
     assert ei.value.code == capi.ERR_BAD_SIZE
+
+
+def test_small_grid_graph_batches_and_history_reallocation(b2s, gpu, oracle):
+    """L2-resident grids run whole batches of PT iterations as one CUDA graph per ping-pong parity (after a first
+    stream-launched batch). Batches of odd and even starting parity, partial batches, a growing error history (its device
+    buffer is reallocated, the captured launches are rebuilt) and a converged time step in between: all bit-exact."""
+    n = (48, 40, 36)
+    o = oracle.Diffusion3D(*n)
+    g = _mk(b2s, *n)
+    g.init_gaussian()
+    for chunk in (3, 128, 129, 300, 1, 700):
+        eo, eg = o.iterate(chunk), g.iterate(chunk)
+        assert np.allclose(eg, eo, rtol=REL_NORM_TOL, atol=0.0), chunk
+        assert np.array_equal(g.get("Htau"), o.get("Htau")), chunk
+    assert g.solve_timestep(1e-7) == pytest.approx(o.solve_timestep(1e-7), rel=1e-12)
+    o.advance_time(); g.advance_time()
+    eo, eg = o.iterate(257), g.iterate(257)
+    assert np.allclose(eg, eo, rtol=REL_NORM_TOL, atol=0.0)
+    assert np.array_equal(g.get("Htau"), o.get("Htau")) and np.array_equal(g.get("Ht"), o.get("Ht"))
+    g.close()
