@@ -241,7 +241,9 @@ struct DeviceCtx {  // one per distinct device of the handle: stream, PT state, 
     int err_hist_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_bar = nullptr;  // cross-device ordering of the plane copies (general decompositions)
-    cudaStream_t copy_stream = nullptr;          // b2s_diff3d_download_state_async
+    cudaStream_t copy_stream = nullptr;          // uploads (b2s_diff3d_upload_state_async)
+    cudaStream_t copy_stream_down = nullptr;     // downloads (b2s_diff3d_download_state_async): PCIe is full duplex, so the two
+                                                 // directions get a stream each and overlap
     cudaEvent_t ev_work = nullptr, ev_down = nullptr, ev_up = nullptr, ev_staged_free = nullptr;
     bool download_pending = false;
 };
@@ -716,6 +718,7 @@ int destroy_impl(b2s_diff3d *h)
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_bar) cudaEventDestroy(d.ev_bar);
         if (d.copy_stream) { cudaStreamSynchronize(d.copy_stream); cudaStreamDestroy(d.copy_stream); }
+        if (d.copy_stream_down) { cudaStreamSynchronize(d.copy_stream_down); cudaStreamDestroy(d.copy_stream_down); }
         if (d.ev_work) cudaEventDestroy(d.ev_work);
         if (d.ev_down) cudaEventDestroy(d.ev_down);
         if (d.ev_up) cudaEventDestroy(d.ev_up);
@@ -1306,6 +1309,7 @@ static int ensure_copy_stream(DeviceCtx &d)
 {
     if (!d.copy_stream) {
         B2S_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+        B2S_CUDA(cudaStreamCreateWithFlags(&d.copy_stream_down, cudaStreamNonBlocking));
         B2S_CUDA(cudaEventCreateWithFlags(&d.ev_work, cudaEventDisableTiming));
         B2S_CUDA(cudaEventCreateWithFlags(&d.ev_down, cudaEventDisableTiming));
         B2S_CUDA(cudaEventCreateWithFlags(&d.ev_up, cudaEventDisableTiming));
@@ -1332,9 +1336,9 @@ int b2s_diff3d_download_state_async(b2s_diff3d *h, int slab, double *Htau_host)
     if (d.download_pending) B2S_CUDA(cudaStreamWaitEvent(d.stream, d.ev_down, 0));  // previous transfer out of stage_out
     B2S_CUDA(cudaMemcpyAsync(s.stage_out, s.buf[cur], bytes, cudaMemcpyDeviceToDevice, d.stream));
     B2S_CUDA(cudaEventRecord(d.ev_work, d.stream));
-    B2S_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev_work, 0));
-    B2S_CUDA(cudaMemcpyAsync(Htau_host, s.stage_out, bytes, cudaMemcpyDeviceToHost, d.copy_stream));
-    B2S_CUDA(cudaEventRecord(d.ev_down, d.copy_stream));
+    B2S_CUDA(cudaStreamWaitEvent(d.copy_stream_down, d.ev_work, 0));
+    B2S_CUDA(cudaMemcpyAsync(Htau_host, s.stage_out, bytes, cudaMemcpyDeviceToHost, d.copy_stream_down));
+    B2S_CUDA(cudaEventRecord(d.ev_down, d.copy_stream_down));
     d.download_pending = true;
     return B2S_OK;
 }
@@ -1386,6 +1390,7 @@ int b2s_diff3d_sync(b2s_diff3d *h)
         B2S_CUDA(cudaSetDevice(d.dev));
         B2S_CUDA(cudaStreamSynchronize(d.stream));
         if (d.copy_stream) B2S_CUDA(cudaStreamSynchronize(d.copy_stream));
+        if (d.copy_stream_down) B2S_CUDA(cudaStreamSynchronize(d.copy_stream_down));
     }
     return B2S_OK;
 }
