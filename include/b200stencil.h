@@ -198,6 +198,9 @@ int b2s_residual2d(const double *u_dev, const double *f_dev, double h, double c,
 /* r_rms = iteration_2DPoisson!(u, f, h, c, res, policy; alpha)  multigrid.jl:245-258 (in place; synchronises). */
 int b2s_iteration2d(double *u_dev, const double *f_dev, double h, double c, double *res_dev, int nx, int ny,
                     double alpha, int policy, double *r_rms_host, void *stream);
+/* NOT provided: iteration_2DPoisson_gs! (multigrid.jl:269-297), the serial lexicographic Gauss-Seidel sweep. It has no call
+ * site in the reference (dead code upstream) and is inherently sequential; the CPU oracle restates it (orc_gs2d_lex) so that
+ * variant B's on-the-fly residual definition can be checked against it, the library does not. */
 /* Variant B smoother: one red-black Gauss-Seidel sweep in place (alpha = 1); r_rms from pre-update residuals. */
 int b2s_rbgs2d(double *u_dev, const double *f_dev, double h, double c, int nx, int ny, double *r_rms_host,
                void *stream);
