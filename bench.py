@@ -439,7 +439,9 @@ def multi_gpu_parity_check(part1, capi, dist, rank, N, dev):
     import numpy as np
     import torch
     from oracle import oracle_lib as O
-    O.build()
+    if rank == 0:  # one rank (re)builds the checker if need be; the others load it afterwards
+        O.build()
+    dist.barrier()
     shape = (64, 64, 34)
     g = part1.Diffusion3D(*shape, nslabs=N, devices=[dev], slab_begin=rank, slab_count=1,
                           halo_mode=capi.HALO_REFERENCE_LAG2, scale_physical_size=True, kernel_variant=capi.KERNEL_TMA)
