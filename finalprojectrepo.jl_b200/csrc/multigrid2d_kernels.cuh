@@ -440,13 +440,28 @@ __global__ void __launch_bounds__(kMGBX) mg_prolong_smooth_kernel(const ProlongS
 // redundantly by neighbouring blocks), so results are bit-identical to them.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTileThreads = 256;
+// B2S_TILE_FG = 1 (experiment, OFF by default): the right-hand side is NOT staged in shared memory; every use reads it from
+// global memory through the read-only path. Two arrays per tile instead of three: the 64x16 tiles of a 1025^2 level need
+// 25-28 KB instead of 41 KB, so 7-8 blocks instead of 5 are resident per SM and the 1105 blocks of that level run in
+// (almost) one wave instead of 1.5. Measured on B200 (profiles/r02_tile_rhs_global_ab.jsonl): bit-identical and 2.7 %
+// SLOWER per 1025^2 V-cycle (0.0796 vs 0.0775 ms) -- the L2 latency of the rhs loads sits in every point's dependency
+// chain and outweighs the extra resident blocks.
+#ifndef B2S_TILE_FG
+#define B2S_TILE_FG 0
+#endif
+#if B2S_TILE_FG
+#define B2S_TILE_RHS(Fsm, s, rhsg, i, j, nx) __ldg((rhsg) + ((size_t)(i) + (size_t)(nx) * (size_t)(j)))
+#else
+#define B2S_TILE_RHS(Fsm, s, rhsg, i, j, nx) (Fsm)[s]
+#endif
 template <int TW, int TH>
 struct TileCfg {
     static constexpr int kTW = TW, kTH = TH;
     static constexpr int kTP = TW + 8;  // shared-memory row pitch (tile + 2*3 halo, padded)
     static constexpr int kTRows = TH + 6;
     static constexpr int kCW = TW / 2 + 3, kCH = TH / 2 + 3;  // coarse window staged by the upward kernel
-    static constexpr size_t kSmemBytes = ((size_t)3 * kTP * kTRows + (size_t)kCW * kCH) * sizeof(double);
+    static constexpr int kArrays = B2S_TILE_FG ? 2 : 3;  // u ping, u pong (, rhs)
+    static constexpr size_t kSmemBytes = ((size_t)kArrays * kTP * kTRows + (size_t)kCW * kCH) * sizeof(double);
 };
 
 struct TileArgs {
@@ -479,28 +494,69 @@ __device__ __forceinline__ void cp_async_wait_all()
 
 // one Jacobi sweep inside shared memory over a window of global coordinates. CHECKED = false: the whole window is
 // known to lie in the interior of the domain (no per-point tests).
+// B2S_TILE_YB = 2 (default; measured -1.3 % per 1025^2 V-cycle, profiles/r02_tile_yblock_ab.jsonl): a thread owns two
+// vertically adjacent points per step -- the
+// column values of rows r-1 .. r+2 are loaded once (4 loads) and shared by both stencils, the index arithmetic is paid
+// once per pair, every shared-memory access stays unit-stride across the lanes (10 loads + 2 stores per 2 points
+// instead of 12 + 2). Window heights are even for every tile shape. Each point is still the unfused kernels' arithmetic.
+#ifndef B2S_TILE_YB
+#define B2S_TILE_YB 2
+#endif
 template <int kTP, bool CHECKED>
 __device__ __forceinline__ void tile_sweep(const double *__restrict__ src, const double *__restrict__ F, double *__restrict__ dst,
-                                           int gx0, int gy0, int wx0, int wy0, int W, int H, int nx, int ny, const Coef &k)
+                                           int gx0, int gy0, int wx0, int wy0, int W, int H, int nx, int ny, const Coef &k,
+                                           const double *__restrict__ rhs_g)
 {
+    (void)F; (void)rhs_g;
     // (gx0, gy0): global coordinates of shared-memory element (0,0); window origin (wx0, wy0), size W x H
     const int s0 = (wy0 - gy0) * kTP + (wx0 - gx0);
+#if B2S_TILE_YB == 2
+    for (int idx = threadIdx.x; idx < W * (H >> 1); idx += kTileThreads) {
+        const int rp = idx / W, c = idx - rp * W;
+        const int r = 2 * rp;
+        const int s = s0 + r * kTP + c;
+        const double a0 = src[s - kTP], a1 = src[s], a2 = src[s + kTP], a3 = src[s + 2 * kTP];
+        double v0 = a1, v1 = a2;
+        bool w0 = true, w1 = true, u0 = true, u1 = true;
+        const int i = wx0 + c, j = wy0 + r;
+        if (CHECKED) {
+            const bool iin = i >= 0 && i < nx, iint = i >= 1 && i <= nx - 2;
+            w0 = iin && j >= 0 && j < ny;
+            w1 = iin && j + 1 >= 0 && j + 1 < ny;
+            u0 = iint && j >= 1 && j <= ny - 2;
+            u1 = iint && j + 1 >= 1 && j + 1 <= ny - 2;
+        }
+        if (u0) {
+            const double res = ((src[s + 1] + src[s - 1] + a2 + a0 - k.C * a1) * k._h2 - B2S_TILE_RHS(F, s, rhs_g, i, j, nx));
+            v0 = a1 + k.w * res;
+        }
+        if (u1) {
+            const double res = ((src[s + kTP + 1] + src[s + kTP - 1] + a3 + a1 - k.C * a2) * k._h2 -
+                                B2S_TILE_RHS(F, s + kTP, rhs_g, i, j + 1, nx));
+            v1 = a2 + k.w * res;
+        }
+        if (w0) dst[s] = v0;
+        if (w1) dst[s + kTP] = v1;
+    }
+#else
     for (int idx = threadIdx.x; idx < W * H; idx += kTileThreads) {
         const int r = idx / W, c = idx - r * W;
         const int s = s0 + r * kTP + c;
         double v = src[s];
         bool upd = true;
+        const int i = wx0 + c, j = wy0 + r;
         if (CHECKED) {
-            const int i = wx0 + c, j = wy0 + r;
             if (i < 0 || j < 0 || i >= nx || j >= ny) continue;
             upd = i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2;
         }
         if (upd) {
-            const double res = ((src[s + 1] + src[s - 1] + src[s + kTP] + src[s - kTP] - k.C * v) * k._h2 - F[s]);
+            const double res = ((src[s + 1] + src[s - 1] + src[s + kTP] + src[s - kTP] - k.C * v) * k._h2 -
+                                B2S_TILE_RHS(F, s, rhs_g, i, j, nx));
             v = v + k.w * res;
         }
         dst[s] = v;
     }
+#endif
 }
 
 template <int TW, int TH>
@@ -510,7 +566,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     constexpr int kTW = Cf::kTW, kTH = Cf::kTH, kTP = Cf::kTP, kTRows = Cf::kTRows, kCW = Cf::kCW, kCH = Cf::kCH;
     (void)kCW; (void)kCH; (void)kTRows;
     extern __shared__ __align__(16) double tsm[];
-    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows;
+    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + (Cf::kArrays - 1) * kTP * kTRows;  // F: only when staged
     const MGCall *cp = a.cp;
     // Levels below the finest get their array pointers from the launch arguments: their staging loads are issued before
     // the call block (done flag, constants) has arrived, which takes one L2 round trip off the critical path of these
@@ -537,7 +593,9 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
             const bool in = jin && i >= 0 && i < nx;
             const size_t p = in ? rowoff + i : 0;
             cp_async8(Ar + c, u + p, in);
+#if !B2S_TILE_FG
             cp_async8(Fr + c, rhs + p, in && frow && c >= 1 && c < kTW + 5);
+#endif
         }
     }
     const int done = a.level == 0 ? 0 : cp->done;
@@ -549,13 +607,13 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
     // block-uniform: does the widest stencil window stay strictly inside the domain?
     const bool inner = X0 - 2 >= 1 && Y0 - 2 >= 1 && X0 + kTW + 1 <= nx - 2 && Y0 + kTH + 1 <= ny - 2;
     if (inner) {
-        tile_sweep<kTP, false>(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k);
+        tile_sweep<kTP, false>(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k, rhs);
         __syncthreads();
-        tile_sweep<kTP, false>(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+        tile_sweep<kTP, false>(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k, rhs);
     } else {
-        tile_sweep<kTP, true>(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k);
+        tile_sweep<kTP, true>(A, F, B, gx0, gy0, X0 - 2, Y0 - 2, kTW + 4, kTH + 4, nx, ny, k, rhs);
         __syncthreads();
-        tile_sweep<kTP, true>(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+        tile_sweep<kTP, true>(B, F, A, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k, rhs);
     }
     __syncthreads();
     // smoothed u out
@@ -575,7 +633,8 @@ __global__ void __launch_bounds__(kTileThreads) mg_down_kernel(const TileArgs a)
         const bool interior = I >= 1 && I <= nxc - 2 && J >= 1 && J <= nyc - 2;
         if (interior) {
             const int s = (2 * r + 3) * kTP + 2 * c + 3;
-            const double v = ((A[s + 1] + A[s - 1] + A[s + kTP] + A[s - kTP] - k.C * A[s]) * k._h2 - F[s]);
+            const double v = ((A[s + 1] + A[s - 1] + A[s + kTP] + A[s - kTP] - k.C * A[s]) * k._h2 -
+                              B2S_TILE_RHS(F, s, rhs, 2 * I, 2 * J, nx));
             a.rc[pc] = v;
             if (apply_bcs) {  // coarse[0,:] = coarse[1,:] ; coarse[nxc-1,:] = coarse[nxc-2,:]
                 if (I == 1) a.rc[(size_t)0 + (size_t)nxc * J] = v;
@@ -613,7 +672,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     (void)kCW; (void)kCH; (void)kTRows;
     extern __shared__ __align__(16) double tsm[];
     __shared__ double red[32];
-    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + 2 * kTP * kTRows, *Cw = tsm + 3 * kTP * kTRows;
+    double *A = tsm, *B = tsm + kTP * kTRows, *F = tsm + (Cf::kArrays - 1) * kTP * kTRows, *Cw = tsm + Cf::kArrays * kTP * kTRows;
     const MGCall *cp = a.cp;
     const double *rhs = a.rhs;
     double *out = a.u_out;
@@ -638,7 +697,9 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
             const bool in = jin && i >= 0 && i < nx;
             const size_t p = in ? rowoff + i : 0;
             cp_async8(Ar + c, a.u_in + p, in);
+#if !B2S_TILE_FG
             cp_async8(Fr + c, rhs + p, in && frow && c >= 1 && c < kTW + 3);
+#endif
         }
     }
     for (int r = threadIdx.x >> 5; r < kCH; r += kTileThreads / 32) {
@@ -668,8 +729,8 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
     }
     __syncthreads();
     const bool inner = X0 - 1 >= 1 && Y0 - 1 >= 1 && X0 + kTW <= nx - 2 && Y0 + kTH <= ny - 2;
-    if (inner) tile_sweep<kTP, false>(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
-    else tile_sweep<kTP, true>(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k);
+    if (inner) tile_sweep<kTP, false>(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k, rhs);
+    else tile_sweep<kTP, true>(A, F, B, gx0, gy0, X0 - 1, Y0 - 1, kTW + 2, kTH + 2, nx, ny, k, rhs);
     __syncthreads();
     double acc = 0.0;
     for (int idx = threadIdx.x; idx < kTW * kTH; idx += kTileThreads) {
@@ -679,7 +740,7 @@ __global__ void __launch_bounds__(kTileThreads) mg_up_kernel(const TileArgs a)
         const int s = (r + 3) * kTP + c + 3;
         double v = B[s];
         if (i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2) {
-            const double res = ((B[s + 1] + B[s - 1] + B[s + kTP] + B[s - kTP] - k.C * v) * k._h2 - F[s]);
+            const double res = ((B[s + 1] + B[s - 1] + B[s + kTP] + B[s - kTP] - k.C * v) * k._h2 - B2S_TILE_RHS(F, s, rhs, i, j, nx));
             acc += res * res;
             v = v + k.w * res;
         }
